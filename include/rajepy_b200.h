@@ -1,0 +1,197 @@
+/*
+ * rajepy_b200 -- C ABI of the B200-native engine for RaJePy's hot path
+ * (jet-grid fill + line-of-sight radiative transfer).
+ *
+ * The reference (SimonP2207/RaJePy) is pure Python/numpy and has NO FFI layer for this
+ * path; its boundary is the Python class JetModel (classes.py:42-1713).  This header is
+ * therefore the interface a maintainer binds from Python with ctypes (see
+ * INTEGRATION.md); each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types, no exceptions.
+ *   - every function returns an int status: 0 = ok, < 0 = error (rjp_strerror()).
+ *   - all buffers are caller-owned DEVICE pointers unless the name ends in _host;
+ *     launches are asynchronous on the cudaStream_t passed as `void* stream`
+ *     (the caller synchronises).  No global mutable state.
+ *   - arrays follow the reference layout: cells (nx, ny, nz) C-order, y = line of
+ *     sight (classes.py:46, :465-474); images (nx, nz); cubes (nchan, nx, nz).
+ *   - a device may hold an x-slab [x_lo, x_hi) of the grid (multi-GPU sharding);
+ *     per-cell buffers then have (x_hi - x_lo) * ny * nz entries and image buffers
+ *     (x_hi - x_lo) * nz.
+ */
+#ifndef RAJEPY_B200_H
+#define RAJEPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RJP_ABI_VERSION 1
+#define RJP_MAX_BURSTS 16
+
+enum {
+  RJP_OK = 0,
+  RJP_ERR_ARG = -1,       /* null pointer / bad dimension / bad enum          */
+  RJP_ERR_CUDA = -2,      /* a CUDA runtime call failed (see rjp_last_cuda_error) */
+  RJP_ERR_CAPACITY = -3,  /* a caller-provided list was too small              */
+  RJP_ERR_UNSUPPORTED = -4
+};
+
+/* Per-cell packed state written by rjp_fill_grid and streamed (once) by
+ * rjp_integrate: 16 bytes = the algorithmic bytes per cell of SURVEY.md 8(d).
+ *   w0: float  n_e0 = n_base * x  [cm^-3] without burst factor; sign bit = red jet (r < 0)
+ *   w1: float  T [K];                                           sign bit = half-filled cell
+ *   w2: int32  (v_los - v_lsr) / v_scale   (INT32_MIN = NaN velocity)
+ *   w3: int32  travel time / t_scale       (seconds from the jet base to the cell)
+ * An all-zero cell is outside the jet.  w0 == 0 (ignoring sign): density invalid;
+ * w1 == 0 or NaN (ignoring sign): temperature invalid (classes.py:891-897, :963-967). */
+typedef struct { uint32_t w0, w1; int32_t w2, w3; } rjp_cell;
+
+/* Everything the grid fill needs (host scalars derived as JetModel.__init__ does,
+ * classes.py:168-242; angles as maths/geometry.py:243-247). */
+typedef struct {
+  int32_t nx, ny, nz;        /* full grid (even, classes.py:201-205)                */
+  int32_t x_lo, x_hi;        /* slab held by this device                            */
+  double cs;                 /* cell size [au]                                      */
+  double w0, r0, mr0, eps;   /* geometry; mr0 = mod_r_0 (geometry.py:12-31)         */
+  double ca, sa, cb, sb;     /* cos/sin(radians(inc-90)), cos/sin(radians(pa))      */
+  double cva, sva, cvb, svb; /* cos/sin(radians(90-inc)), cos/sin(radians(-pa))     */
+  double R1, R2;             /* disc radii [au]                                     */
+  double q_n, q_x, q_T, q_v; /* axial power-law indices                             */
+  double qd_n, qd_x, qd_T, qd_v; /* cross-sectional indices                         */
+  double n0, x0, T0, v0;     /* base values (cm^-3, -, K, km/s)                     */
+  double f_rb;               /* mlr_rj / mlr_bj (classes.py:228-229, :895)          */
+  double gm_over_au;         /* G * M_star * MSOL / au  (physics.py:90)             */
+  double rot_sign;           /* +1 CCW, -1 CW (classes.py:1069-1071)                */
+  double v_lsr;              /* km/s                                                */
+  double au_m, year_s;       /* scipy.constants.au / .year                          */
+  double au_cm;              /* au * 1e2: the temperature quirk (classes.py:957)    */
+  /* 2F1 connection constants for the travel time when qd_v != 0 (geometry.py:166-171):
+   * 2F1(a, b; b+1; z), a = qd_v, b = (1 - q_v + eps*qd_v)/eps                      */
+  double hyp_b;              /* b                                                   */
+  double hyp_c1;             /* b / (b - a)                                         */
+  double hyp_c2;             /* Gamma(b+1) Gamma(a-b) / Gamma(a)                    */
+  int32_t hyp_degenerate;    /* 1: b-a (near-)integer -> series only                */
+  int32_t reserved0;
+  double t_scale;            /* seconds per count of rjp_cell.w3                    */
+  double v_scale;            /* km/s per count of rjp_cell.w2                       */
+} rjp_model;
+
+/* One Gaussian ejection burst of one jet (classes.py:399-463). */
+typedef struct {
+  double t0;        /* peak time [s]                                   */
+  double amp;       /* (peak_jml - ss_jml) / ss_jml  = chi - 1         */
+  double inv2s2;    /* 1 / (2 sigma^2), sigma = hl * 2 / (2 sqrt(2 ln 2)) [s^-2] */
+} rjp_burst;
+
+typedef struct {
+  double time;                       /* model time [s] (JetModel.time)           */
+  int32_t n_blue, n_red;
+  rjp_burst blue[RJP_MAX_BURSTS];
+  rjp_burst red[RJP_MAX_BURSTS];
+} rjp_epoch;
+
+/* Continuum integration constants (classes.py:1116-1120, :1395-1399). */
+typedef struct {
+  double em_scale;      /* cs * au / pc                                           */
+  double tau_scale;     /* 0.018 * cs * au * 100                                  */
+  double t_exponent;    /* -1.5 (q_T == 0: van Hoof g_ff) or -1.35 (Reynolds g_ff folded) */
+} rjp_continuum;
+
+/* LTE recombination-line constants (classes.py:1159-1189; maths/rrls.py). */
+typedef struct {
+  double nu0;           /* rest frequency [Hz] (rrls.py:14-29)                    */
+  double dopp;          /* 1000 / c   (physics.py:547-558)                        */
+  double width_g;       /* sqrt(2 k / (m_atom c^2)): sigma*sqrt(2) = width_g*sqrt(T)*nu0_cell */
+  double stark;         /* 8.2 (n/100)^4.5 (1 + 2.25 dn/n) / 2  (rrls.py:86-101)  */
+  double kappa0;        /* 1.0991132675738456e-17 n^2 f (X mu'/m_amu) cs au 100 / sqrt(pi) */
+  double en_over_k;     /* Z^2 E_n / k_cgs  [K]  (rrls.py:386)                    */
+  double h_over_k;      /* h / k [K s]                                            */
+  double v_lsr;         /* km/s                                                   */
+} rjp_line;
+
+/* Per-channel host-prepared scalars, each a DEVICE array of nchan doubles. */
+typedef struct {
+  const double* dnu;     /* nu_k - nu0 [Hz]                                        */
+  const double* nu;      /* nu_k [Hz]                                              */
+  const double* cff;     /* tau_ff(nu_k) = cff_k * K  (nu^-2 g_ff or 11.95 nu^-2.1)*/
+  const double* aff;     /* S_ff = aff_k * Tmean * (1 - exp(-tau_ff))  [Jy/pixel]  */
+  const double* bnu;     /* 2 h nu^3 / c^2 [cgs] * 1e-3 * Omega_pix / 1e-26        */
+} rjp_channels;
+
+const char* rjp_strerror(int status);
+const char* rjp_last_cuda_error(void);
+int rjp_abi_version(void);
+/* sizeof() of the ABI structs, so a ctypes binding can verify its mirror. */
+int rjp_struct_sizes(int32_t* model, int32_t* epoch, int32_t* continuum, int32_t* line,
+                     int32_t* channels, int32_t* cell);
+
+/* Grid fill (K1+K2).  Replaces JetModel.fill_factor/areas (classes.py:571-784) and
+ * the per-cell property chain ts/number_density/ion_fraction/temperature/vel
+ * (classes.py:838-1099; maths/geometry.py:121-336).
+ *   nverts [slab cells]  : number of cell vertices inside the jet (0..8), bit-exact
+ *                          apart from the vertices reported in `ties`
+ *   cells  [slab cells]  : packed state
+ *   ties   [tie_capacity*3] int32 (I,J,K) lattice indices of vertices whose inside
+ *                          test is too close to call in device arithmetic; *n_ties
+ *                          (device) receives the number found (may exceed capacity:
+ *                          then re-run with a larger list)
+ *   status [4] int32 device: [0] cells whose travel time overflowed t_scale,
+ *                          [1] cells whose velocity overflowed v_scale          */
+int rjp_fill_grid(const rjp_model* m_host, uint8_t* nverts, rjp_cell* cells,
+                  int32_t* ties, int32_t tie_capacity, int32_t* n_ties,
+                  int32_t* status, void* stream);
+
+/* Apply host-resolved vertex decisions: for n cells (flat slab indices `cell_idx`,
+ * device) set nverts to `new_count` (device, uint8) and recompute the packed state. */
+int rjp_patch_cells(const rjp_model* m_host, const int64_t* cell_idx,
+                    const uint8_t* new_count, int32_t n, uint8_t* nverts,
+                    rjp_cell* cells, int32_t* status, void* stream);
+
+/* Full-precision 3-D property planes on demand (float64, NaN outside the jet where the
+ * reference has NaN), for the JetModel properties the plotting code reads. */
+enum {
+  RJP_FIELD_FILL_FACTOR = 0,  /* classes.py:667-668,763 */
+  RJP_FIELD_AREAS = 1,        /* classes.py:669,764     */
+  RJP_FIELD_R = 2, RJP_FIELD_W = 3, RJP_FIELD_PHI = 4,     /* classes.py:515-541 */
+  RJP_FIELD_REFF = 5,         /* classes.py:543-557     */
+  RJP_FIELD_TRAVEL = 6,       /* seconds; JetModel.ts = time - this (classes.py:838-859) */
+  RJP_FIELD_ND_BASE = 7,      /* classes.py:872-897 (without chi) */
+  RJP_FIELD_XI = 8,           /* classes.py:910-936     */
+  RJP_FIELD_TEMP = 9,         /* classes.py:942-969     */
+  RJP_FIELD_VX = 10, RJP_FIELD_VLOS = 11, RJP_FIELD_VZ = 12, /* classes.py:1009-1095 */
+  RJP_FIELD_CHI = 13,         /* classes.py:861-870 (needs epoch) */
+  RJP_FIELD_COUNT = 14
+};
+int rjp_cell_field(const rjp_model* m_host, const rjp_epoch* ep_host,
+                   const uint8_t* nverts, int32_t field, double* out, void* stream);
+
+/* Fused line-of-sight pass (K3+K4+K5): every cell of the slab is read once.
+ * Replaces emission_measure (classes.py:1101-1128), optical_depth_ff (:1353-1447),
+ * the nanmean temperature of intensity_ff (:1471-1473), optical_depth_rrl (:1130-1229)
+ * and intensity_rrl/flux_rrl (:1231-1351).
+ *   em, kff, tsum [nxs*nz] double, tcount [nxs*nz] int32 (always written)
+ *   line/ch may be NULL/nchan = 0 for a continuum-only pass; otherwise
+ *   tau_rrl and/or flux_rrl ([nchan][nxs][nz] double) may each be NULL.
+ *   contsub: 0 -> flux_rrl includes S_ff (what Pipeline requests, classes.py:2450).  */
+int rjp_integrate(const rjp_model* m_host, const rjp_epoch* ep_host,
+                  const rjp_continuum* cont_host, const rjp_cell* cells,
+                  double* em, double* kff, double* tsum, int32_t* tcount,
+                  const rjp_line* line_host, const rjp_channels* ch_host, int32_t nchan,
+                  int32_t contsub, double* tau_rrl, double* flux_rrl, void* stream);
+
+/* Continuum epilogue (K5) for nfreq frequencies from one pass' kff/tsum/tcount:
+ *   tau[f] = cff[f] * kff;  I[f] = iff[f] * Tmean * (1 - exp(-tau));  S[f] = I * omega_jy
+ * (classes.py:1427-1432, :1484-1488, :1531-1533).  cff/iff are DEVICE arrays [nfreq];
+ * any of tau/intensity/flux ([nfreq][npix]) may be NULL.                             */
+int rjp_continuum_images(const double* kff, const double* tsum, const int32_t* tcount,
+                         int64_t npix, const double* cff, const double* iff,
+                         double omega_jy, int32_t nfreq, double* tau, double* intensity,
+                         double* flux, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAJEPY_B200_H */

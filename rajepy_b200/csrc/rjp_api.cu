@@ -1,0 +1,128 @@
+// extern "C" entry points declared in include/rajepy_b200.h: argument validation,
+// launch, CUDA error capture.  No state besides the thread-local last-error string.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/rajepy_b200.h"
+
+extern "C" {
+int rjp_launch_fill(const rjp_model*, uint8_t*, rjp_cell*, int32_t*, int32_t, int32_t*,
+                    int32_t*, cudaStream_t);
+int rjp_launch_patch(const rjp_model*, const int64_t*, const uint8_t*, int32_t, uint8_t*,
+                     rjp_cell*, int32_t*, cudaStream_t);
+int rjp_launch_field(const rjp_model*, const rjp_epoch*, const uint8_t*, int32_t, double*,
+                     cudaStream_t);
+int rjp_launch_integrate(const rjp_model*, const rjp_epoch*, const rjp_continuum*,
+                         const rjp_cell*, double*, double*, double*, int32_t*,
+                         const rjp_line*, const rjp_channels*, int, int, double*, double*,
+                         cudaStream_t);
+int rjp_launch_continuum_images(const double*, const double*, const int32_t*, int64_t,
+                                const double*, const double*, double, int, double*, double*,
+                                double*, cudaStream_t);
+}
+
+static thread_local char g_cuda_err[256] = "";
+
+static int check_launch(int st) {
+  if (st != RJP_OK) return st;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e),
+             cudaGetErrorString(e));
+    return RJP_ERR_CUDA;
+  }
+  return RJP_OK;
+}
+
+static bool model_ok(const rjp_model* m) {
+  return m && m->nx > 0 && m->ny > 0 && m->nz > 0 && m->x_lo >= 0 && m->x_hi <= m->nx &&
+         m->x_lo < m->x_hi && m->cs > 0.0 && m->t_scale > 0.0 && m->v_scale > 0.0;
+}
+
+extern "C" const char* rjp_strerror(int status) {
+  switch (status) {
+    case RJP_OK: return "ok";
+    case RJP_ERR_ARG: return "invalid argument";
+    case RJP_ERR_CUDA: return "CUDA runtime error";
+    case RJP_ERR_CAPACITY: return "caller-provided list too small";
+    case RJP_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown status";
+  }
+}
+
+extern "C" const char* rjp_last_cuda_error(void) { return g_cuda_err; }
+
+extern "C" int rjp_abi_version(void) { return RJP_ABI_VERSION; }
+
+extern "C" int rjp_struct_sizes(int32_t* model, int32_t* epoch, int32_t* continuum,
+                                int32_t* line, int32_t* channels, int32_t* cell) {
+  if (model) *model = (int32_t)sizeof(rjp_model);
+  if (epoch) *epoch = (int32_t)sizeof(rjp_epoch);
+  if (continuum) *continuum = (int32_t)sizeof(rjp_continuum);
+  if (line) *line = (int32_t)sizeof(rjp_line);
+  if (channels) *channels = (int32_t)sizeof(rjp_channels);
+  if (cell) *cell = (int32_t)sizeof(rjp_cell);
+  return RJP_OK;
+}
+
+extern "C" int rjp_fill_grid(const rjp_model* m, uint8_t* nverts, rjp_cell* cells,
+                             int32_t* ties, int32_t tie_capacity, int32_t* n_ties,
+                             int32_t* status, void* stream) {
+  if (!model_ok(m) || !nverts || !cells || !n_ties || !status || tie_capacity < 0 ||
+      (tie_capacity > 0 && !ties))
+    return RJP_ERR_ARG;
+  return check_launch(rjp_launch_fill(m, nverts, cells, ties, tie_capacity, n_ties, status,
+                                      (cudaStream_t)stream));
+}
+
+extern "C" int rjp_patch_cells(const rjp_model* m, const int64_t* cell_idx,
+                               const uint8_t* new_count, int32_t n, uint8_t* nverts,
+                               rjp_cell* cells, int32_t* status, void* stream) {
+  if (!model_ok(m) || n < 0 || (n > 0 && (!cell_idx || !new_count)) || !nverts || !cells ||
+      !status)
+    return RJP_ERR_ARG;
+  return check_launch(rjp_launch_patch(m, cell_idx, new_count, n, nverts, cells, status,
+                                       (cudaStream_t)stream));
+}
+
+extern "C" int rjp_cell_field(const rjp_model* m, const rjp_epoch* ep, const uint8_t* nverts,
+                              int32_t field, double* out, void* stream) {
+  if (!model_ok(m) || !ep || !nverts || !out || field < 0 || field >= RJP_FIELD_COUNT)
+    return RJP_ERR_ARG;
+  if (ep->n_blue < 0 || ep->n_blue > RJP_MAX_BURSTS || ep->n_red < 0 ||
+      ep->n_red > RJP_MAX_BURSTS)
+    return RJP_ERR_ARG;
+  return check_launch(rjp_launch_field(m, ep, nverts, field, out, (cudaStream_t)stream));
+}
+
+extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_continuum* ct,
+                             const rjp_cell* cells, double* em, double* kff, double* tsum,
+                             int32_t* tcount, const rjp_line* ln, const rjp_channels* ch,
+                             int32_t nchan, int32_t contsub, double* tau_rrl,
+                             double* flux_rrl, void* stream) {
+  if (!model_ok(m) || !ep || !ct || !cells || !em || !kff || !tsum || !tcount || nchan < 0)
+    return RJP_ERR_ARG;
+  if (ep->n_blue < 0 || ep->n_blue > RJP_MAX_BURSTS || ep->n_red < 0 ||
+      ep->n_red > RJP_MAX_BURSTS)
+    return RJP_ERR_ARG;
+  if (nchan > 0) {
+    if (!ln || !ch || !ch->dnu || !ch->nu || !ch->cff || !ch->aff || !ch->bnu)
+      return RJP_ERR_ARG;
+    if (!tau_rrl && !flux_rrl) return RJP_ERR_ARG;
+  }
+  return check_launch(rjp_launch_integrate(m, ep, ct, cells, em, kff, tsum, tcount, ln, ch,
+                                           nchan, contsub, tau_rrl, flux_rrl,
+                                           (cudaStream_t)stream));
+}
+
+extern "C" int rjp_continuum_images(const double* kff, const double* tsum,
+                                    const int32_t* tcount, int64_t npix, const double* cff,
+                                    const double* iff, double omega_jy, int32_t nfreq,
+                                    double* tau, double* intensity, double* flux,
+                                    void* stream) {
+  if (!kff || !tsum || !tcount || npix < 0 || nfreq < 0 || (nfreq > 0 && (!cff || !iff)))
+    return RJP_ERR_ARG;
+  return check_launch(rjp_launch_continuum_images(kff, tsum, tcount, npix, cff, iff, omega_jy,
+                                                  nfreq, tau, intensity, flux,
+                                                  (cudaStream_t)stream));
+}

@@ -1,0 +1,302 @@
+// Device-side math of the RaJePy hot path for sm_100a.
+//
+// Everything here is fp64: the grid fill decides bit-exact integer vertex counts and
+// feeds 1e-6-relative line-of-sight sums; B200's FP64 pipe (64 lanes/SM) is half the
+// FP32 rate, and all heavy functions below run only for the few per cent of cells
+// that lie inside the jet.  Reference citations are relative to the reference root.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include "../../include/rajepy_b200.h"
+
+namespace rjp {
+
+__device__ __forceinline__ double dnan() { return CUDART_NAN; }
+
+// ---------------------------------------------------------------- geometry
+// maths/geometry.py:181-209 -> :212-260 ('yx') -> :266-302.  numpy never fuses a
+// multiply with an add, so every product and sum is rounded separately (__dmul_rn /
+// __dadd_rn are never contracted into FMAs).
+struct Rw { double r, w, x1, y2; };
+
+__device__ __forceinline__ Rw xyz_to_rw(const rjp_model& m, double x, double y, double z) {
+  Rw o;
+  o.x1 = __dadd_rn(__dmul_rn(m.cb, x), __dmul_rn(m.sb, z));
+  double z1 = __dsub_rn(__dmul_rn(m.cb, z), __dmul_rn(m.sb, x));
+  o.y2 = __dsub_rn(__dmul_rn(m.ca, y), __dmul_rn(m.sa, z1));
+  o.r = __dadd_rn(__dmul_rn(m.sa, y), __dmul_rn(m.ca, z1));
+  o.w = __dsqrt_rn(__dadd_rn(__dmul_rn(o.x1, o.x1), __dmul_rn(o.y2, o.y2)));
+  return o;
+}
+
+// maths/geometry.py:34-61: ((|r| + mr0) - r0) / mr0, or |r| / r0 when mr0 is falsy.
+__device__ __forceinline__ double rho_of(const rjp_model& m, double abs_r) {
+  if (m.mr0 != 0.0) return __ddiv_rn(__dsub_rn(__dadd_rn(abs_r, m.mr0), m.r0), m.mr0);
+  return __ddiv_rn(abs_r, m.r0);
+}
+
+// x ** q with numpy semantics (x ** 0 == 1 for every x, NaN for negative base and
+// non-integer exponent); the q == 0 / q == 1 shortcuts only save time.
+__device__ __forceinline__ double powq(double x, double q) {
+  if (q == 0.0) return 1.0;
+  if (q == 1.0) return x;
+  return pow(x, q);
+}
+
+// Corner coordinate of lattice index i along an axis of n cells: cs * (i - n//2)
+// (classes.py:497-499); exact integer -> one rounding.
+__device__ __forceinline__ double corner(double cs, int i, int n) {
+  return __dmul_rn(cs, (double)(i - n / 2));
+}
+
+// ---------------------------------------------------------------- vertex test
+// classes.py:661-666: inside <=> w_0 * rho(r)**eps >= w  and  |r| >= r_0.
+// Returns bit0 = decision in device arithmetic, bit1 = "too close to call": the
+// decision could differ from numpy's (different pow implementation, or a vertex
+// coordinate formed as cs*(i-h)+cs instead of cs*(i+1-h)); the host re-decides those
+// with the reference's own numpy expression per (cell, corner).
+__device__ __forceinline__ int vertex_inside(const rjp_model& m, double x, double y,
+                                             double z) {
+  Rw g = xyz_to_rw(m, x, y, z);
+  const double ar = fabs(g.r);
+  const double scale = fabs(x) + fabs(y) + fabs(z);
+  const double tol = 3.5527136788005009e-15;  // 2^-48
+  const bool in_r = ar >= m.r0;
+  const bool r_band = fabs(ar - m.r0) <= tol * (scale + m.r0);
+  if (!in_r && !r_band) return 0;
+  const double rh = rho_of(m, ar);
+  bool in_w, w_band = false;
+  bool decided = false;
+  if (rh > 0.0 && rh < 1e30 && g.w > 0.0) {
+    // cheap certain decision from an fp32 estimate (relative error << 1e-3)
+    float wa = (float)m.w0 * __powf((float)rh, (float)m.eps);
+    float wf = (float)g.w;
+    if (wa > wf * 1.001f) { in_w = true; decided = true; }
+    else if (wa < wf * 0.999f) { in_w = false; decided = true; }
+  }
+  if (!decided) {
+    double wr = __dmul_rn(m.w0, pow(rh, m.eps));
+    in_w = wr >= g.w;
+    w_band = fabs(wr - g.w) <= tol * (scale + g.w + fabs(wr));
+  }
+  int inside = (in_w && in_r) ? 1 : 0;
+  int tie = ((w_band && (in_r || r_band)) || (r_band && (in_w || w_band))) ? 2 : 0;
+  return inside | tie;
+}
+
+// ---------------------------------------------------------------- 2F1(a, b; b+1; z), z < 0
+// scipy.special.hyp2f1 call of maths/geometry.py:168-171 (a = q^d_v,
+// b = (1 - q_v + eps q^d_v)/eps).  Three regimes: Gauss series (|z| <= 1/2), Pfaff
+// transformation z -> z/(z-1) in (1/3, 2/3] (|z| <= 2, or always when b - a is an
+// integer), and the 1/z connection formula (A&S 15.3.7) whose second 2F1 collapses to
+// 1 because c - b = 1.
+__device__ inline double hyp2f1_bp1(const rjp_model& m, double z) {
+  const double a = m.qd_v, b = m.hyp_b;
+  if (a == 0.0 || z == 0.0) return 1.0;
+  const double az = -z;
+  if (!(az > 0.0)) return dnan();  // z > 0 needs R_2 < R_1: unsupported
+  if (az <= 0.5) {
+    double term = 1.0, sum = 1.0;
+    for (int n = 0; n < 400; ++n) {
+      term *= (a + n) / (n + 1.0) * z;
+      double add = term * b / (b + n + 1.0);
+      sum += add;
+      if (fabs(add) <= 1e-17 * fabs(sum)) break;
+    }
+    return sum;
+  }
+  if (az <= 2.0 || m.hyp_degenerate) {
+    const double zeta = az / (1.0 + az);
+    double term = 1.0, sum = 1.0;
+    for (int n = 0; n < 4000000; ++n) {
+      term *= (a + n) / (b + 1.0 + n) * zeta;
+      sum += term;
+      if (fabs(term) <= 1e-17 * fabs(sum)) break;
+    }
+    return pow(1.0 + az, -a) * sum;
+  }
+  const double u = 1.0 / z;
+  const double d = a - b;
+  double term = 1.0, sum = 1.0;
+  for (int n = 0; n < 400; ++n) {
+    term *= (a + n) / (n + 1.0) * u;
+    double add = term * d / (d + n + 1.0);
+    sum += add;
+    if (fabs(add) <= 1e-17 * fabs(sum)) break;
+  }
+  return m.hyp_c1 * pow(az, -a) * sum + m.hyp_c2 * pow(az, -b);
+}
+
+// ---------------------------------------------------------------- per-cell physics
+struct CellProps {
+  double r, w, phi, reff;      // centroid jet coordinates (classes.py:515-557)
+  double travel;               // s (classes.py:852 / geometry.py:121-178)
+  double nd, xi, temp;         // unmasked-by-ff values with the 0/inf -> NaN rule
+  double vx, vlos_rel, vz;     // km/s after rotation to the observer; vlos_rel excludes v_lsr
+};
+
+// maths/geometry.py:150-173, SI units.
+__device__ inline double travel_indef(const rjp_model& m, double r_si, double w_si) {
+  const double W0 = m.w0 * m.au_m, R0 = m.r0 * m.au_m, MR0 = m.mr0 * m.au_m;
+  const double R1 = m.R1 * m.au_m, R2 = m.R2 * m.au_m, V0 = m.v0 * 1e3;
+  const double cst = powq(MR0, m.q_v) / (V0 * (1.0 - m.q_v + m.eps * m.qd_v));
+  const double rad = r_si + MR0 - R0;
+  const double p1 = powq(rad, 1.0 - m.q_v);
+  if (m.qd_v == 0.0) return cst * p1;
+  // r_eff with |r| in SI (geometry.py:157)
+  const double rhos = (MR0 != 0.0) ? (fabs(r_si) + MR0 - R0) / MR0 : fabs(r_si) / R0;
+  const double reff = R1 + ((R2 - R1) * w_si) / (W0 * pow(rhos, m.eps));
+  const double p2 = pow(reff / R1, -m.qd_v);
+  double p3, p4;
+  if (w_si == 0.0) {
+    p3 = 1.0;
+    p4 = 1.0 + m.qd_v / (1.0 - m.q_v);
+  } else {
+    const double A = (R1 * W0 * pow(rad, m.eps)) / (w_si * pow(MR0, m.eps));
+    p3 = pow(A / (R2 - R1) + 1.0, m.qd_v);
+    p4 = hyp2f1_bp1(m, A / (R1 - R2));
+  }
+  return cst * p1 * p2 * p3 * p4;
+}
+
+__device__ __forceinline__ double clean(double v) {  // 0 -> NaN, +-inf -> NaN
+  return (v == 0.0 || isinf(v)) ? dnan() : v;
+}
+
+__device__ inline CellProps cell_props(const rjp_model& m, int ix, int iy, int iz,
+                                       bool want_phi) {
+  CellProps o;
+  const double h = m.cs / 2.0;
+  const double xc = __dadd_rn(corner(m.cs, ix, m.nx), h);
+  const double yc = __dadd_rn(corner(m.cs, iy, m.ny), h);
+  const double zc = __dadd_rn(corner(m.cs, iz, m.nz), h);
+  Rw g = xyz_to_rw(m, xc, yc, zc);
+  o.r = g.r;
+  o.w = g.w;
+  const double q = g.y2 / g.w;  // sin(phi); NaN on the axis like arcsin(0/0)
+  if (want_phi) {
+    double p = asin(q);
+    o.phi = (g.x1 < 0.0) ? (CUDART_PI - p) : p;
+  } else {
+    o.phi = 0.0;
+  }
+  const double ar = fabs(g.r);
+  const double rho_c = rho_of(m, ar);
+  // geometry.py:336 with |r| (classes.py:549-555)
+  o.reff = m.R1 + ((m.R2 - m.R1) * g.w) / (m.w0 * pow(rho_c, m.eps));
+  // base shift: classes.py:848-850
+  double rt = ar;
+  if (ar < m.r0 && (ar + h) >= m.r0) rt = (m.r0 + ar + h) / 2.0;
+  const double rho_t = rho_of(m, rt);
+  const double x_re = o.reff / m.R1;
+  // classes.py:889-897
+  double nd = clean(m.n0 * powq(rho_t, m.q_n) * powq(x_re, m.qd_n));
+  if (g.r < 0.0) nd *= m.f_rb;
+  o.nd = isinf(nd) ? dnan() : nd;
+  // classes.py:928-934
+  o.xi = clean(m.x0 * powq(rho_t, m.q_x) * powq(x_re, m.qd_x));
+  // classes.py:957-967: |r| in cm compared with r_0 in au (reference quirk, kept)
+  double rT = ar * m.au_cm;
+  if (rT < m.r0 && (rT + h) >= m.r0) rT = (m.r0 + rT + h) / 2.0;
+  o.temp = clean(m.T0 * powq(rho_of(m, rT), m.q_T) * powq(x_re, m.qd_T));
+  // classes.py:1056-1093, physics.py:90
+  double vz = clean(m.v0 * powq(rho_t, m.q_v) * powq(x_re, m.qd_v));
+  const double sgn = (g.r > 0.0) ? 1.0 : ((g.r < 0.0) ? -1.0 : 0.0);
+  vz *= sgn;
+  const double vrot = sqrt(m.gm_over_au / o.reff) * pow(rho_c, -m.eps) / 1e3;
+  const double vxj = -vrot * q * m.rot_sign;
+  const double vyj = vrot * (g.x1 / g.w) * m.rot_sign;
+  // xyz_rotate(vx, vy, vz, 90 - inc, -pa, 'xy'): geometry.py:249-258
+  const double y1 = m.cva * vyj - m.sva * vz;
+  const double z1 = m.sva * vyj + m.cva * vz;
+  o.vx = m.cvb * vxj + m.svb * z1;
+  o.vlos_rel = y1;
+  o.vz = m.cvb * z1 - m.svb * vxj;
+  // classes.py:852: t_rw(r_shifted, w) * year
+  const double F1 = travel_indef(m, rt * m.au_m, g.w * m.au_m);
+  const double F0 = travel_indef(m, m.r0 * m.au_m, g.w * m.au_m);
+  o.travel = (F1 - F0) / m.year_s * m.year_s;
+  return o;
+}
+
+// Pack one in-jet cell (nverts > 0) into the 16-byte state.
+__device__ inline rjp_cell pack_cell(const rjp_model& m, const CellProps& p, int nverts,
+                                     int32_t* status) {
+  rjp_cell c;
+  const bool red = p.r < 0.0;
+  const bool half = nverts < 8;
+  double ne0 = p.nd * p.xi;
+  float f0 = 0.f;
+  int32_t tq = 0;
+  if (ne0 == ne0 && !isinf(ne0) && p.travel == p.travel) {
+    f0 = (float)ne0;
+    if (isinf(f0)) f0 = 0.f;
+    double tc = rint(p.travel / m.t_scale);
+    if (fabs(tc) > 2147483000.0) {
+      atomicAdd(&status[0], 1);
+      tc = copysign(2147483000.0, tc);
+    }
+    tq = (int32_t)tc;
+  }
+  float tf = 0.f;
+  if (p.temp == p.temp && p.temp > 0.0) {
+    tf = (float)p.temp;
+    if (isinf(tf)) tf = 0.f;
+  }
+  int32_t vq = INT32_MIN;
+  if (p.vlos_rel == p.vlos_rel) {
+    double vc = rint(p.vlos_rel / m.v_scale);
+    if (fabs(vc) > 2147483000.0) {
+      atomicAdd(&status[1], 1);
+      vc = copysign(2147483000.0, vc);
+    }
+    vq = (int32_t)vc;
+  }
+  c.w0 = __float_as_uint(f0) | (red ? 0x80000000u : 0u);
+  c.w1 = __float_as_uint(tf) | (half ? 0x80000000u : 0u);
+  c.w2 = vq;
+  c.w3 = tq;
+  return c;
+}
+
+// classes.py:442-448 divided by the steady-state rate: chi = 1 + sum amp_i exp(...)
+__device__ __forceinline__ double burst_chi(const rjp_burst* b, int n, double t_launch) {
+  double chi = 1.0;
+  for (int i = 0; i < n; ++i) {
+    const double d = t_launch - b[i].t0;
+    chi += b[i].amp * exp(-(d * d) * b[i].inv2s2);
+  }
+  return chi;
+}
+
+// ---------------------------------------------------------------- Faddeeva (Voigt)
+#include "rjp_weideman.inc"
+__constant__ double c_weideman[RJP_WEIDEMAN_N] = {RJP_WEIDEMAN_COEFFS};
+
+// Re w(x + iy), y > 0: Weideman's rational approximation; the degree-(N-1) polynomial
+// with real coefficients is evaluated at the complex point Z with the real two-term
+// recurrence b_k = a_k + 2Re(Z) b_{k+1} - |Z|^2 b_{k+2} (2 DFMA per coefficient).
+// Replaces scipy.special.wofz at maths/rrls.py:353.
+__device__ __forceinline__ double faddeeva_re(double x, double y) {
+  const double L = RJP_WEIDEMAN_L;
+  const double dr = L + y, nr = L - y;        // L - iz = dr - i x ; L + iz = nr + i x
+  const double inv = 1.0 / (dr * dr + x * x);
+  const double Zr = (nr * dr - x * x) * inv;
+  const double Zi = (2.0 * L) * x * inv;
+  const double s = 2.0 * Zr, q = Zr * Zr + Zi * Zi;
+  double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < RJP_WEIDEMAN_N - 1; ++k) {
+    const double b0 = fma(s, b1, fma(-q, b2, c_weideman[k]));
+    b2 = b1;
+    b1 = b0;
+  }
+  const double pr = c_weideman[RJP_WEIDEMAN_N - 1] + Zr * b1 - q * b2;
+  const double pi = Zi * b1;
+  const double ur = dr * inv, ui = x * inv;   // 1/(L - iz)
+  const double u2r = ur * ur - ui * ui, u2i = 2.0 * ur * ui;
+  return 2.0 * (pr * u2r - pi * u2i) + ur * 0.56418958354775628695;  // 1/sqrt(pi)
+}
+
+}  // namespace rjp

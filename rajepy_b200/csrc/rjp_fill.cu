@@ -1,0 +1,181 @@
+// Grid fill for sm_100a: K1 (8-vertex inside test, classes.py:657-669) fused with K2
+// (per-cell state, classes.py:838-1095).
+//
+// One CTA owns a TX x TY x TZ brick of cells.  The (TX+1)(TY+1)(TZ+1) lattice vertices
+// of the brick are tested ONCE each (instead of 8 times, as the reference's eight grid
+// passes do) and their inside bits are staged in shared memory; every cell then sums
+// its eight corner bits.  Lanes run along z, the contiguous axis, so the 16-byte
+// state stores and the 1-byte count stores of a warp are fully coalesced (512 B / 32 B).
+// No input is read from HBM: the pass is bounded by the 17 B/cell it writes and by
+// the fp64 pipe (vertex transform + sqrt); `pow` runs only for vertices that an fp32
+// estimate cannot decide and for cells inside the jet.
+#include "rjp_device.cuh"
+
+namespace rjp {
+
+constexpr int TX = 4, TY = 8, TZ = 32;
+constexpr int FILL_THREADS = 256;
+constexpr int NVERT = (TX + 1) * (TY + 1) * (TZ + 1);
+
+__global__ void __launch_bounds__(FILL_THREADS)
+fill_grid_kernel(const rjp_model m, uint8_t* __restrict__ nverts,
+                 rjp_cell* __restrict__ cells, int32_t* __restrict__ ties,
+                 int32_t tie_capacity, int32_t* __restrict__ n_ties,
+                 int32_t* __restrict__ status) {
+  __shared__ uint8_t s_in[NVERT];
+  const int nxs = m.x_hi - m.x_lo;
+  const int tiles_z = (m.nz + TZ - 1) / TZ;
+  const int tiles_y = (m.ny + TY - 1) / TY;
+  int t = blockIdx.x;
+  const int tz0 = (t % tiles_z) * TZ; t /= tiles_z;
+  const int ty0 = (t % tiles_y) * TY; t /= tiles_y;
+  const int tx0 = m.x_lo + t * TX;
+
+  for (int v = threadIdx.x; v < NVERT; v += FILL_THREADS) {
+    const int lz = v % (TZ + 1);
+    const int ly = (v / (TZ + 1)) % (TY + 1);
+    const int lx = v / ((TZ + 1) * (TY + 1));
+    const int I = tx0 + lx, J = ty0 + ly, K = tz0 + lz;
+    int res = 0;
+    if (I <= m.x_hi && J <= m.ny && K <= m.nz) {
+      res = vertex_inside(m, corner(m.cs, I, m.nx), corner(m.cs, J, m.ny),
+                          corner(m.cs, K, m.nz));
+      // report each near-tie once: by the brick that owns the vertex (lower faces),
+      // or by the last brick at the slab / grid upper faces
+      const bool own = (lx < TX || I == m.x_hi) && (ly < TY || J == m.ny) &&
+                       (lz < TZ || K == m.nz);
+      if ((res & 2) && own) {
+        const int slot = atomicAdd(n_ties, 1);
+        if (slot < tie_capacity) {
+          ties[4 * slot + 0] = I;
+          ties[4 * slot + 1] = J;
+          ties[4 * slot + 2] = K;
+          ties[4 * slot + 3] = res & 1;
+        }
+      }
+    }
+    s_in[v] = (uint8_t)(res & 1);
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int wrp = threadIdx.x >> 5;  // == local y
+#pragma unroll
+  for (int lx = 0; lx < TX; ++lx) {
+    const int ix = tx0 + lx, iy = ty0 + wrp, iz = tz0 + lane;
+    if (ix >= m.x_hi || iy >= m.ny || iz >= m.nz) continue;
+    int cnt = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int vx = lx + (c & 1), vy = wrp + ((c >> 1) & 1), vz = lane + (c >> 2);
+      cnt += s_in[(vx * (TY + 1) + vy) * (TZ + 1) + vz];
+    }
+    const size_t idx = ((size_t)(ix - m.x_lo) * m.ny + iy) * m.nz + iz;
+    nverts[idx] = (uint8_t)cnt;
+    rjp_cell c = {0u, 0u, 0, 0};
+    if (cnt > 0) c = pack_cell(m, cell_props(m, ix, iy, iz, false), cnt, status);
+    reinterpret_cast<uint4*>(cells)[idx] = make_uint4(c.w0, c.w1, (uint32_t)c.w2,
+                                                       (uint32_t)c.w3);
+  }
+}
+
+__global__ void patch_cells_kernel(const rjp_model m, const int64_t* __restrict__ cell_idx,
+                                   const uint8_t* __restrict__ new_count, int32_t n,
+                                   uint8_t* __restrict__ nverts,
+                                   rjp_cell* __restrict__ cells,
+                                   int32_t* __restrict__ status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t idx = cell_idx[i];
+  const int iz = (int)(idx % m.nz);
+  const int iy = (int)((idx / m.nz) % m.ny);
+  const int ix = m.x_lo + (int)(idx / ((int64_t)m.nz * m.ny));
+  const int cnt = new_count[i];
+  nverts[idx] = (uint8_t)cnt;
+  rjp_cell c = {0u, 0u, 0, 0};
+  if (cnt > 0) c = pack_cell(m, cell_props(m, ix, iy, iz, false), cnt, status);
+  cells[idx] = c;
+}
+
+__global__ void __launch_bounds__(256)
+cell_field_kernel(const rjp_model m, const rjp_epoch ep, const uint8_t* __restrict__ nverts,
+                  int field, double* __restrict__ out) {
+  const size_t ncell = (size_t)(m.x_hi - m.x_lo) * m.ny * m.nz;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < ncell;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int cnt = nverts[idx];
+    double v;
+    if (field == RJP_FIELD_FILL_FACTOR) {
+      v = (cnt == 8) ? 1.0 : (cnt > 0 ? 0.5 : dnan());
+    } else if (field == RJP_FIELD_AREAS) {
+      v = cnt > 0 ? 1.0 : dnan();
+    } else {
+      const bool masked = field >= RJP_FIELD_ND_BASE && field <= RJP_FIELD_VZ;
+      if (masked && cnt == 0) {
+        v = dnan();
+      } else {
+        const int iz = (int)(idx % m.nz);
+        const int iy = (int)((idx / m.nz) % m.ny);
+        const int ix = m.x_lo + (int)(idx / ((size_t)m.nz * m.ny));
+        CellProps p = cell_props(m, ix, iy, iz, field == RJP_FIELD_PHI);
+        switch (field) {
+          case RJP_FIELD_R: v = p.r; break;
+          case RJP_FIELD_W: v = p.w; break;
+          case RJP_FIELD_PHI: v = p.phi; break;
+          case RJP_FIELD_REFF: v = p.reff; break;
+          case RJP_FIELD_TRAVEL: v = p.travel; break;
+          case RJP_FIELD_ND_BASE: v = p.nd; break;
+          case RJP_FIELD_XI: v = p.xi; break;
+          case RJP_FIELD_TEMP: v = p.temp; break;
+          case RJP_FIELD_VX: v = p.vx; break;
+          case RJP_FIELD_VLOS: v = p.vlos_rel + m.v_lsr; break;
+          case RJP_FIELD_VZ: v = p.vz; break;
+          case RJP_FIELD_CHI: {
+            const double tl = ep.time - p.travel;
+            v = (p.r < 0.0) ? burst_chi(ep.red, ep.n_red, tl)
+                            : burst_chi(ep.blue, ep.n_blue, tl);
+            break;
+          }
+          default: v = dnan();
+        }
+      }
+    }
+    out[idx] = v;
+  }
+}
+
+}  // namespace rjp
+
+using namespace rjp;
+
+extern "C" int rjp_launch_fill(const rjp_model* m, uint8_t* nverts, rjp_cell* cells,
+                               int32_t* ties, int32_t tie_capacity, int32_t* n_ties,
+                               int32_t* status, cudaStream_t stream) {
+  const int nxs = m->x_hi - m->x_lo;
+  const long long tiles = (long long)((nxs + TX - 1) / TX) * ((m->ny + TY - 1) / TY) *
+                          ((m->nz + TZ - 1) / TZ);
+  if (tiles <= 0 || tiles > 2147483647LL) return RJP_ERR_ARG;
+  fill_grid_kernel<<<(unsigned)tiles, FILL_THREADS, 0, stream>>>(
+      *m, nverts, cells, ties, tie_capacity, n_ties, status);
+  return RJP_OK;
+}
+
+extern "C" int rjp_launch_patch(const rjp_model* m, const int64_t* cell_idx,
+                                const uint8_t* new_count, int32_t n, uint8_t* nverts,
+                                rjp_cell* cells, int32_t* status, cudaStream_t stream) {
+  if (n <= 0) return RJP_OK;
+  patch_cells_kernel<<<(n + 127) / 128, 128, 0, stream>>>(*m, cell_idx, new_count, n,
+                                                         nverts, cells, status);
+  return RJP_OK;
+}
+
+extern "C" int rjp_launch_field(const rjp_model* m, const rjp_epoch* ep,
+                                const uint8_t* nverts, int32_t field, double* out,
+                                cudaStream_t stream) {
+  const size_t ncell = (size_t)(m->x_hi - m->x_lo) * m->ny * m->nz;
+  size_t blocks = (ncell + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  if (blocks == 0) return RJP_OK;
+  cell_field_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*m, *ep, nverts, field, out);
+  return RJP_OK;
+}

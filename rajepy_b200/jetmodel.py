@@ -1,0 +1,1082 @@
+"""
+`JetModel` -- drop-in replacement for the reference's `RaJePy.classes.JetModel`
+(classes.py:42-1713) whose grid fill and line-of-sight radiative transfer run in
+hand-written sm_100a CUDA kernels behind the C ABI of include/rajepy_b200.h.
+
+Same constructor, properties, method names, argument meaning, return shapes
+(numpy float64; 3-D fields (nx, ny, nz) with NaN outside the jet; images (nx, nz);
+cubes (nfreq, nx, nz)) and error conventions as the reference.  Host code only derives
+scalars (fp64, scipy.constants), owns device buffers through torch, and calls the
+library through ctypes.  There is NO CPU fallback: without a CUDA device or without
+the compiled library every compute call raises.
+
+Multi-GPU: with `shard=(rank, world)` the model fills and integrates only an x-slab of
+the grid and `gather=True` methods all-gather the image tiles over
+torch.distributed (NCCL on GPUs); no other exchange exists on this path.
+"""
+import os
+import pickle
+import sys
+import time as _time
+
+import numpy as np
+import scipy.constants as con
+
+from . import _cabi
+from . import hostmath as hm
+from . import logger
+from .sharding import gather_x, slab_bounds
+
+_TIE_CAPACITY = 1 << 16
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class JetModel:
+    """
+    Class to handle physical model of an ionised jet from a young stellar object
+    (API of the reference class, classes.py:42).
+    """
+    _arr_indexing = 'ij'  # numpy.meshgrid indexing type (classes.py:46)
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def load_model(cls, model_file, **kwargs):
+        """Load a model saved with `save` (classes.py:48-88)."""
+        model_file = os.path.expanduser(model_file)
+        with open(model_file, 'rb') as f:
+            loaded = pickle.load(f)
+        if 'log' in loaded and loaded['log'] is not None:
+            new_jm = cls(loaded["params"], log=loaded['log'], **kwargs)
+        else:
+            dcy_ = os.path.expanduser('~')
+            new_jm = cls(loaded["params"], log=logger.Log(dcy_ + os.sep + 'temp.log'),
+                         **kwargs)
+        if loaded.get('ffs') is not None:
+            new_jm._adopt_fill_factor(loaded['ffs'])
+        new_jm.time = loaded['time']
+        return new_jm
+
+    @staticmethod
+    def lz_to_grid_dims(params):
+        """classes.py:90-122"""
+        return hm.lz_to_grid_dims(params)
+
+    @staticmethod
+    def py_to_dict(py_file):
+        """Parameter file (python module exposing `params`) -> dict (classes.py:124-142).
+        Unlike the reference's validator (miscellaneous/functions.py:127-190) a missing
+        properties.n_0 is accepted: it is always overwritten (classes.py:234-242) and the
+        reference's own example file omits it."""
+        if not os.path.exists(py_file):
+            raise FileNotFoundError(py_file + " does not exist")
+        import importlib.util
+        name = "_rajepy_params_" + str(abs(hash(os.path.abspath(py_file))))
+        spec = importlib.util.spec_from_file_location(name, py_file)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        err = check_model_params(getattr(mod, "params", None))
+        if err is not None:
+            raise err
+        return mod.params
+
+    def __init__(self, params, log=None, device=None, shard=None):
+        if isinstance(params, dict):
+            self._params = params
+        elif isinstance(params, str):
+            self._params = JetModel.py_to_dict(params)
+        else:
+            raise TypeError("Supplied arg params must be dict or file path (str)")
+
+        p = self._params
+        self._name = p['target']['name']
+        self._csize = p['grid']['c_size']
+
+        # automatically calculated parameters (classes.py:168-180)
+        mr0 = hm.mod_r_0(p['geometry']['opang'], p['geometry']['epsilon'],
+                         p['geometry']['w_0'])
+        qn = hm.q_n(p["geometry"]["epsilon"], p["power_laws"]["q_v"])
+        qtau = hm.q_tau(p["geometry"]["epsilon"], p["power_laws"]["q_x"], qn,
+                        p["power_laws"]["q_T"])
+        p["geometry"]["mod_r_0"] = mr0
+        p["power_laws"]["q_n"] = qn
+        p["power_laws"]["q_tau"] = qtau
+
+        if log is not None:
+            self._log = log
+        else:
+            self._log = logger.Log(os.path.expanduser('~') + os.sep + 'temp.log',
+                                   verbose=True)
+
+        # grid dimensions (classes.py:188-213)
+        if p['grid']['l_z'] is not None:
+            nx, ny, nz = JetModel.lz_to_grid_dims(p)
+            self.log.add_entry("INFO",
+                               'For a (bipolar) jet length of {:.1f}", cell '
+                               'size of {:.2f}au and distance of {:.0f}pc, a '
+                               'grid size of (n_x, n_y, n_z) = ({}, {}, {}) '
+                               'voxels is calculated'
+                               ''.format(p['grid']['l_z'], p["grid"]["c_size"],
+                                         p["target"]["dist"], nx, ny, nz))
+        else:
+            nx = (p['grid']['n_x'] + 1) // 2 * 2
+            ny = (p['grid']['n_y'] + 1) // 2 * 2
+            nz = (p['grid']['n_z'] + 1) // 2 * 2
+        p['grid']['n_x'], p['grid']['n_y'], p['grid']['n_z'] = nx, ny, nz
+        self._nx, self._ny, self._nz = int(nx), int(ny), int(nz)
+
+        # steady-state mass-loss rates (classes.py:228-242)
+        self._ss_jml_rb_frac = p["properties"]["mlr_rj"] / p["properties"]["mlr_bj"]
+        self._ss_jml_bj = p["properties"]["mlr_bj"] * (1.989e30 / con.year)
+        self._ss_jml_rj = self._ss_jml_bj * self._ss_jml_rb_frac
+        p["properties"]["n_0"] = hm.n_0_from_mlr(
+            p["properties"]["mlr_bj"], p["properties"]["v_0"], p["geometry"]["w_0"],
+            p["properties"]["mu"], p["power_laws"]["q^d_n"], p["power_laws"]["q^d_v"],
+            p["target"]["R_1"], p["target"]["R_2"])
+
+        # ejection bursts (classes.py:244-264)
+        self._bursts = {'R': [], 'B': []}
+        self._jml_t_bj = lambda t: self._ss_jml_bj
+        self._jml_t_rj = lambda t: self._ss_jml_rj
+        self._ejections = {}
+        for idx, ejn_t0 in enumerate(p['ejection']['t_0']):
+            which = p['ejection']['which'][idx]
+            if 'R' in which:
+                self.add_ejection_event(ejn_t0 * con.year,
+                                        self._ss_jml_rj * p['ejection']['chi'][idx],
+                                        p['ejection']['hl'][idx] * con.year, which='R')
+            if 'B' in which:
+                self.add_ejection_event(ejn_t0 * con.year,
+                                        self._ss_jml_bj * p['ejection']['chi'][idx],
+                                        p['ejection']['hl'][idx] * con.year, which='B')
+
+        self._time = 0. * con.year
+
+        # device side
+        self._device_arg = device
+        if shard is None:
+            shard = (0, 1)
+        self._rank, self._world = int(shard[0]), int(shard[1])
+        self._x_lo, self._x_hi = slab_bounds(self._nx, self._rank, self._world)
+        self._dev = None       # dict of device buffers once filled
+        self._fields = {}      # cached host copies of 3-D property grids
+        self._overrides = {}   # user-assigned grids (setters)
+        self._cont = None      # cached continuum pass (device tensors)
+        self._line = None      # cached line pass
+        self._timings = {}
+
+    # ------------------------------------------------------------------ text table
+    def __str__(self):
+        """Same table as the reference (classes.py:268-361); it becomes the FITS HISTORY."""
+        p = self.params
+        h = ['Parameter', 'Value']
+        d = [('epsilon', format(p['geometry']['epsilon'], '+.3f')),
+             ('opang', format(p['geometry']['opang'], '+.0f') + ' deg'),
+             ('q_v', format(p['power_laws']['q_v'], '+.3f')),
+             ('q_T', format(p['power_laws']['q_T'], '+.3f')),
+             ('q_x', format(p['power_laws']['q_x'], '+.3f')),
+             ('q_n', format(p['power_laws']['q_n'], '+.3f')),
+             ('q^d_v', format(p['power_laws']['q^d_v'], '+.3f')),
+             ('q^d_T', format(p['power_laws']['q^d_T'], '+.3f')),
+             ('q^d_x', format(p['power_laws']['q^d_x'], '+.3f')),
+             ('q^d_n', format(p['power_laws']['q^d_n'], '+.3f')),
+             ('q_tau', format(p['power_laws']['q_tau'], '+.3f')),
+             ('cell', format(p['grid']['c_size'], '.1f') + ' au'),
+             ('w_0', format(p['geometry']['w_0'], '.2f') + ' au'),
+             ('r_0', format(p['geometry']['r_0'], '.2f') + ' au'),
+             ('v_0', format(p['properties']['v_0'], '.0f') + ' km/s'),
+             ('x_0', format(p['properties']['x_0'], '.3f')),
+             ('n_0', format(p['properties']['n_0'], '.3e') + ' cm^-3'),
+             ('T_0', format(p['properties']['T_0'], '.0e') + ' K'),
+             ('f_R2B', format(self._ss_jml_rb_frac, '.2e')),
+             ('i', format(p['geometry']['inc'], '+.1f') + ' deg'),
+             ('theta', format(p['geometry']['pa'], '+.1f') + ' deg'),
+             ('D', format(p['target']['dist'], '+.0f') + ' pc'),
+             ('M*', format(p['target']['M_star'], '+.1f') + ' Msol'),
+             ('R_1', format(p['target']['R_1'], '+.1f') + ' au'),
+             ('R_2', format(p['target']['R_2'], '+.1f') + ' au')]
+        if len(p['ejection']['t_0']) > 0:
+            d.append(('t_now', format(self.time / con.year, '+.3f') + ' yr'))
+
+        c1 = max(len(s) for s in [h[0]] + [r[0] for r in d]) + 2
+        c2 = max(len(s) for s in [h[1]] + [r[1] for r in d]) + 2
+        width = c1 + c2 + 3
+        hline = width * '-'
+
+        def row(cols, widths):
+            return '|' + '|'.join(format(c, '^' + str(w)) for c, w in zip(cols, widths)) + '|\n'
+
+        s = hline + '\n' + '/' + format('JET MODEL', '^' + str(width - 2)) + '/\n' + hline + '\n'
+        s += row(h, (c1, c2)) + hline + '\n'
+        for line_ in d:
+            s += row(line_, (c1, c2))
+        s += hline + '\n'
+        s += '/' + format('BURSTS', '^' + str(width - 2)) + '/\n' + hline + '\n'
+        db = [(format(t, '.2f'), format(p["ejection"]["hl"][i], '.2f'),
+               format(p["ejection"]["chi"][i], '.2f'))
+              for i, t in enumerate(p["ejection"]["t_0"])]
+        if len(db) == 0:
+            return s + '|' + format(' None ', '-^' + str(width - 2)) + '|\n' + hline + '\n'
+        b1 = b2 = b3 = (width - 4) // 3
+        if (width - 4) % 3 > 0:
+            b1 += 1
+            if (width - 4) % 3 == 2:
+                b2 += 1
+        for line_ in (['t_0', 'FWHM', 'chi'], ['[yr]', '[yr]', '']):
+            s += row(line_, (b1, b2, b3))
+        s += hline + '\n'
+        for line_ in db:
+            s += row(line_, (b1, b2, b3))
+        return s + hline + '\n'
+
+    # ------------------------------------------------------------------ simple attributes
+    @property
+    def los_axis(self):
+        if self._arr_indexing == 'ij':
+            return 1
+        elif self._arr_indexing == 'xy':
+            return 0
+        raise ValueError(f"Unknown numpy array indexing ({self._arr_indexing})")
+
+    @property
+    def time(self):
+        """Model time in seconds"""
+        return self._time
+
+    @time.setter
+    def time(self, new_time):
+        self._time = new_time
+
+    @property
+    def log(self):
+        return self._log
+
+    @log.setter
+    def log(self, new_log):
+        self._log = new_log
+
+    @property
+    def csize(self):
+        return self._csize
+
+    @property
+    def nx(self):
+        return self._nx
+
+    @property
+    def ny(self):
+        return self._ny
+
+    @property
+    def nz(self):
+        return self._nz
+
+    @property
+    def params(self):
+        return self._params
+
+    @property
+    def name(self):
+        return self._name
+
+    @property
+    def ejections(self):
+        return self._ejections
+
+    @property
+    def slab(self):
+        """x-range [x_lo, x_hi) of the grid held by this process."""
+        return self._x_lo, self._x_hi
+
+    def ss_jml(self, which):
+        """classes.py:1694-1702"""
+        if which == 'R':
+            return self._ss_jml_rj
+        elif which == 'B':
+            return self._ss_jml_bj
+        elif 'R' in which and 'B' in which:
+            return self._ss_jml_rj + self._ss_jml_bj
+        raise ValueError("which must be one of 'R', 'B', or 'RB'")
+
+    def jml_t(self, which):
+        """Callable t [s] -> jet mass-loss rate [kg/s] (classes.py:383-397)"""
+        def inner_func(t):
+            jml = 0.
+            if 'R' in which:
+                jml += self._jml_t_rj(t)
+            if 'B' in which:
+                jml += self._jml_t_bj(t)
+            return jml
+        return inner_func
+
+    def add_ejection_event(self, t_0, peak_jml, half_life, which):
+        """Gaussian ejection burst (classes.py:399-463).  t_0, half_life in s,
+        peak_jml in kg/s, which in ('R', 'B')."""
+        assert which in ('R', 'B')
+        if len(self._bursts[which]) >= _cabi.MAX_BURSTS:
+            raise ValueError(f"at most {_cabi.MAX_BURSTS} bursts per jet are supported")
+        ss_jml = self._ss_jml_bj if which == 'B' else self._ss_jml_rj
+        amp = peak_jml - ss_jml
+        sigma = half_life * 2. / (2. * np.sqrt(2. * np.log(2.)))
+        prev = self._jml_t_rj if which == 'R' else self._jml_t_bj
+
+        def func2(t, _prev=prev, _amp=amp, _t0=t_0, _sigma=sigma):
+            return _prev(t) + _amp * np.exp(-(t - _t0) ** 2. / (2. * _sigma ** 2.))
+
+        if which == 'R':
+            self._jml_t_rj = func2
+        else:
+            self._jml_t_bj = func2
+        self._bursts[which].append((float(t_0), float(amp / ss_jml),
+                                    float(1. / (2. * sigma ** 2.))))
+        self._ejections[str(len(self._ejections) + 1)] = {
+            't_0': t_0, 'peak_jml': peak_jml, 'half_life': half_life, 'which': which}
+        self._cont = None
+        self._line = None
+
+    # ------------------------------------------------------------------ index/coordinate grids
+    @property
+    def indices(self):
+        """classes.py:465-474 (host numpy; never needed by the CUDA path)"""
+        return tuple(np.meshgrid(np.arange(self.nx), np.arange(self.ny), np.arange(self.nz),
+                                 indexing=self._arr_indexing))
+
+    @property
+    def ix(self):
+        return self.indices[0]
+
+    @property
+    def iy(self):
+        return self.indices[1]
+
+    @property
+    def iz(self):
+        return self.indices[2]
+
+    @property
+    def grid(self):
+        """Corner coordinates in au (classes.py:488-501)"""
+        ix, iy, iz = self.indices
+        return (self.csize * (ix - self.nx // 2), self.csize * (iy - self.ny // 2),
+                self.csize * (iz - self.nz // 2))
+
+    @property
+    def xx(self):
+        return self.grid[0]
+
+    @property
+    def yy(self):
+        return self.grid[1]
+
+    @property
+    def zz(self):
+        return self.grid[2]
+
+    @property
+    def xs(self):
+        return self.csize * (np.arange(self.nx) - self.nx // 2)
+
+    @property
+    def ys(self):
+        return self.csize * (np.arange(self.ny) - self.ny // 2)
+
+    @property
+    def zs(self):
+        return self.csize * (np.arange(self.nz) - self.nz // 2)
+
+    @property
+    def grid_rwp(self):
+        return self._field('r'), self._field('w'), self._field('phi')
+
+    @property
+    def rr(self):
+        return self._field('r')
+
+    @property
+    def ww(self):
+        return self._field('w')
+
+    @property
+    def pp(self):
+        return self._field('phi')
+
+    @property
+    def rreff(self):
+        return self._field('reff')
+
+    # ------------------------------------------------------------------ device plumbing
+    def _device(self):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _cabi.EngineError(
+                "rajepy_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if self._device_arg is not None:
+            return torch.device(self._device_arg)
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def _stream(self):
+        return _torch().cuda.current_stream(self._device()).cuda_stream
+
+    def _model_struct(self, t_scale, v_scale):
+        p = self._params
+        g, pl, pr, tg = p["geometry"], p["power_laws"], p["properties"], p["target"]
+        m = _cabi.Model()
+        m.nx, m.ny, m.nz = self._nx, self._ny, self._nz
+        m.x_lo, m.x_hi = self._x_lo, self._x_hi
+        m.cs = float(self._csize)
+        m.w0, m.r0, m.mr0, m.eps = (float(g["w_0"]), float(g["r_0"]), float(g["mod_r_0"]),
+                                    float(g["epsilon"]))
+        m.ca, m.sa, m.cb, m.sb = hm.rotation_trig(g["inc"] - 90., g["pa"])
+        m.cva, m.sva, m.cvb, m.svb = hm.rotation_trig(90. - g["inc"], -g["pa"])
+        m.R1, m.R2 = float(tg["R_1"]), float(tg["R_2"])
+        m.q_n, m.q_x, m.q_T, m.q_v = (float(pl["q_n"]), float(pl["q_x"]), float(pl["q_T"]),
+                                      float(pl["q_v"]))
+        m.qd_n, m.qd_x, m.qd_T, m.qd_v = (float(pl["q^d_n"]), float(pl["q^d_x"]),
+                                          float(pl["q^d_T"]), float(pl["q^d_v"]))
+        m.n0, m.x0, m.T0, m.v0 = (float(pr["n_0"]), float(pr["x_0"]), float(pr["T_0"]),
+                                  float(pr["v_0"]))
+        m.f_rb = float(self._ss_jml_rb_frac)
+        m.gm_over_au = float(con.G * tg["M_star"] * hm.MSOL / con.au)
+        m.rot_sign = 1.0 if g["rotation"].lower() == 'ccw' else -1.0
+        m.v_lsr = float(tg["v_lsr"])
+        m.au_m, m.year_s, m.au_cm = float(con.au), float(con.year), float(con.au * 1e2)
+        a = m.qd_v
+        b = (1. - m.q_v + m.eps * a) / m.eps
+        m.hyp_b = b
+        m.hyp_c1 = m.hyp_c2 = 0.0
+        m.hyp_degenerate = 1
+        if a != 0.0:
+            if tg["R_2"] <= tg["R_1"]:
+                raise ValueError("q^d_v != 0 requires R_2 > R_1")
+            from scipy.special import gamma, rgamma
+            d = b - a
+            if abs(d - round(d)) > 1e-3:
+                m.hyp_degenerate = 0
+                m.hyp_c1 = b / (b - a)
+                m.hyp_c2 = float(gamma(b + 1.) * gamma(a - b) * rgamma(a))
+        m.t_scale, m.v_scale = float(t_scale), float(v_scale)
+        return m
+
+    def _scale_guess(self):
+        """Fixed-point scales of the packed state: 2^31 counts span +-4x a host estimate
+        of the largest travel time / line-of-sight speed inside the grid (the fill reports
+        overflows, in which case the scales are widened and the fill repeated)."""
+        p = self._params
+        g, pl, pr, tg = p["geometry"], p["power_laws"], p["properties"], p["target"]
+        half = 0.5 * self._csize * np.array([self._nx, self._ny, self._nz]) + self._csize
+        r_max = float(np.sqrt(np.sum(half ** 2)))
+        mr0, r0 = g["mod_r_0"], g["r_0"]
+        rad0 = mr0 * con.au
+        rad1 = (r_max + mr0 - r0) * con.au
+        qv = pl["q_v"]
+        cst = rad0 ** qv / (pr["v_0"] * 1e3 * (1. - qv + g["epsilon"] * pl["q^d_v"]))
+        t_est = abs(cst * (abs(rad1) ** (1. - qv) - rad0 ** (1. - qv)))
+        spread = max(tg["R_2"] / tg["R_1"], 1.0) ** abs(pl["q^d_v"])
+        t_est = max(t_est * spread * 2.0, r_max * con.au / (pr["v_0"] * 1e3), 1.0)
+        rho_lo = max((max(r0 - self._csize, 0.) + mr0 - r0) / mr0, 1e-3) if mr0 else 1.0
+        rho_hi = (r_max + mr0 - r0) / mr0 if mr0 else r_max / r0
+        v_ax = abs(pr["v_0"]) * max(rho_lo ** qv, rho_hi ** qv) * spread
+        v_rot = np.sqrt(con.G * tg["M_star"] * hm.MSOL / (tg["R_1"] * con.au)) / 1e3 * \
+            max(rho_lo ** -g["epsilon"], 1.0)
+        v_est = max(v_ax + v_rot, 1.0)
+        return 4.0 * t_est / 2 ** 31, 4.0 * v_est / 2 ** 31
+
+    def _epoch_struct(self):
+        e = _cabi.Epoch()
+        e.time = float(self._time)
+        e.n_blue, e.n_red = len(self._bursts['B']), len(self._bursts['R'])
+        for key, arr in (('B', e.blue), ('R', e.red)):
+            for i, (t0, amp, inv2s2) in enumerate(self._bursts[key]):
+                arr[i].t0, arr[i].amp, arr[i].inv2s2 = t0, amp, inv2s2
+        return e
+
+    def _ensure_filled(self):
+        """Run the grid fill (K1+K2) once; resolve near-tie vertices on the host with
+        the reference's own numpy expression so that the counts are bit-exact."""
+        if self._dev is not None:
+            return self._dev
+        if self._overrides:
+            raise NotImplementedError("user-assigned grids (ts/ion_fraction/temperature/"
+                                      "vel setters) are not supported by the CUDA path")
+        torch = _torch()
+        lib = _cabi.load()
+        dev = self._device()
+        ncell = (self._x_hi - self._x_lo) * self._ny * self._nz
+        t0 = _time.time()
+        if self.log:
+            self._log.add_entry(mtype="INFO",
+                                entry="Calculating cells' fill factors/projected areas")
+        with torch.cuda.device(dev):
+            nverts = torch.empty(ncell, dtype=torch.uint8, device=dev)
+            cells = torch.empty((ncell, 4), dtype=torch.int32, device=dev)
+            ties = torch.empty((_TIE_CAPACITY, 4), dtype=torch.int32, device=dev)
+            counters = torch.zeros(8, dtype=torch.int32, device=dev)  # [0] n_ties, [4:8] status
+            t_scale, v_scale = self._scale_guess()
+            tie_cap = _TIE_CAPACITY
+            for attempt in range(6):
+                counters.zero_()
+                m = self._model_struct(t_scale, v_scale)
+                st = lib.rjp_fill_grid(m, nverts.data_ptr(), cells.data_ptr(),
+                                       ties.data_ptr(), tie_cap, counters.data_ptr(),
+                                       counters.data_ptr() + 16, self._stream())
+                _cabi.check(st, "rjp_fill_grid")
+                c = counters.cpu().numpy()
+                if c[4] > 0:
+                    t_scale *= 64.0
+                elif c[5] > 0:
+                    v_scale *= 64.0
+                elif c[0] > tie_cap:
+                    tie_cap = int(c[0]) + 1024
+                    ties = torch.empty((tie_cap, 4), dtype=torch.int32, device=dev)
+                else:
+                    break
+            else:
+                raise _cabi.EngineError("grid fill: fixed-point scales did not converge")
+            n_ties = int(c[0])
+            self._dev = {"nverts": nverts, "cells": cells, "model": m, "device": dev,
+                         "n_ties": n_ties, "n_patched": 0}
+            if n_ties > 0:
+                self._resolve_ties(ties[:n_ties].cpu().numpy().astype(np.int64))
+        if self.log:
+            self.log.add_entry(mtype="INFO",
+                               entry=_time.strftime('Finished in %Hh%Mm%Ss',
+                                                    _time.gmtime(_time.time() - t0)))
+        return self._dev
+
+    def _resolve_ties(self, ties):
+        """Vertices whose inside test the device could not call: decide every
+        (cell, corner) that touches them exactly as classes.py:658-666 does -- corner
+        coordinate cs*(i - n//2) + {0|cs}, maths/geometry.py:181-209 and :96-118 in numpy
+        -- and patch the cells whose count changes."""
+        torch = _torch()
+        lib = _cabi.load()
+        d = self._dev
+        g = self._params["geometry"]
+        cs = self._csize
+        I, J, K, dec = ties[:, 0], ties[:, 1], ties[:, 2], ties[:, 3]
+        ny, nz = self._ny, self._nz
+        delta = {}
+        for a in (0, 1):
+            for b in (0, 1):
+                for c in (0, 1):
+                    i, j, k = I - a, J - b, K - c
+                    ok = (i >= self._x_lo) & (i < self._x_hi) & (j >= 0) & (j < ny) & \
+                         (k >= 0) & (k < nz)
+                    if not ok.any():
+                        continue
+                    ii, jj, kk = i[ok], j[ok], k[ok]
+                    x = cs * (ii - self._nx // 2) + (cs if a else 0.)
+                    y = cs * (jj - self._ny // 2) + (cs if b else 0.)
+                    z = cs * (kk - self._nz // 2) + (cs if c else 0.)
+                    rv, wv = hm.xyz_to_rwp(x, y, z, g["inc"], g["pa"])[:2]
+                    with np.errstate(all='ignore'):
+                        wrv = hm.w_r(rv, g["w_0"], g["mod_r_0"], g["r_0"], g["epsilon"])
+                    ref = ((wrv >= wv) & (np.abs(rv) >= g["r_0"])).astype(np.int64)
+                    diff = ref - dec[ok]
+                    flat = ((ii - self._x_lo) * ny + jj) * nz + kk
+                    for f, df in zip(flat[diff != 0], diff[diff != 0]):
+                        delta[int(f)] = delta.get(int(f), 0) + int(df)
+        delta = {f: v for f, v in delta.items() if v != 0}
+        d["n_patched"] = len(delta)
+        if not delta:
+            return
+        dev = d["device"]
+        idx = torch.tensor(sorted(delta), dtype=torch.int64, device=dev)
+        old = d["nverts"][idx].to(torch.int64)
+        new = old + torch.tensor([delta[f] for f in sorted(delta)], dtype=torch.int64,
+                                 device=dev)
+        if int(new.min()) < 0 or int(new.max()) > 8:
+            raise _cabi.EngineError("tie resolution produced an impossible vertex count")
+        new8 = new.to(torch.uint8)
+        status = torch.zeros(4, dtype=torch.int32, device=dev)
+        st = lib.rjp_patch_cells(d["model"], idx.data_ptr(), new8.data_ptr(), idx.numel(),
+                                 d["nverts"].data_ptr(), d["cells"].data_ptr(),
+                                 status.data_ptr(), self._stream())
+        _cabi.check(st, "rjp_patch_cells")
+        if int(status[:2].sum()) > 0:
+            raise _cabi.EngineError("fixed-point overflow while patching cells")
+
+    def _adopt_fill_factor(self, ffs):
+        """Resume path (classes.py:78-84): take fill factors from a saved model instead
+        of recomputing them.  Counts 1..7 are not recoverable from ff = 0.5; any value in
+        that range gives the same physics (ff is all the integrators use)."""
+        torch = _torch()
+        ffs = np.asarray(ffs, dtype=np.float64)
+        if ffs.shape != (self._nx, self._ny, self._nz):
+            raise ValueError("saved fill factors do not match the grid dimensions")
+        saved_overrides, self._overrides = self._overrides, {}
+        self._dev = None
+        d = self._ensure_filled()
+        self._overrides = saved_overrides
+        sl = ffs[self._x_lo:self._x_hi].reshape(-1)
+        want = np.where(sl == 1.0, 8, np.where(sl > 0, 4, 0)).astype(np.uint8)
+        have = d["nverts"].cpu().numpy()
+        cls_have = np.where(have == 8, 8, np.where(have > 0, 4, 0))
+        diff = np.flatnonzero(cls_have != want)
+        if diff.size:
+            lib = _cabi.load()
+            dev = d["device"]
+            idx = torch.from_numpy(diff.astype(np.int64)).to(dev)
+            new8 = torch.from_numpy(want[diff]).to(dev)
+            status = torch.zeros(4, dtype=torch.int32, device=dev)
+            st = lib.rjp_patch_cells(d["model"], idx.data_ptr(), new8.data_ptr(),
+                                     idx.numel(), d["nverts"].data_ptr(),
+                                     d["cells"].data_ptr(), status.data_ptr(), self._stream())
+            _cabi.check(st, "rjp_patch_cells")
+        self._fields.clear()
+        self._cont = self._line = None
+
+    def n_verts_inside(self, gather=True):
+        """Number of cell vertices inside the jet, uint8 (nx, ny, nz): the integer the
+        reference forms at classes.py:657-666 before mapping it to fill factors."""
+        d = self._ensure_filled()
+        t = d["nverts"].view(self._x_hi - self._x_lo, self._ny, self._nz)
+        if gather and self._world > 1:
+            t = gather_x(t, self._nx, self._rank, self._world, dim=0)
+        return t.cpu().numpy()
+
+    def _field_device(self, name):
+        torch = _torch()
+        lib = _cabi.load()
+        d = self._ensure_filled()
+        dev = d["device"]
+        ncell = d["nverts"].numel()
+        out = torch.empty(ncell, dtype=torch.float64, device=dev)
+        ep = self._epoch_struct()
+        st = lib.rjp_cell_field(d["model"], ep, d["nverts"].data_ptr(), _cabi.FIELDS[name],
+                                out.data_ptr(), self._stream())
+        _cabi.check(st, "rjp_cell_field")
+        return out.view(self._x_hi - self._x_lo, self._ny, self._nz)
+
+    def _field(self, name, cache=True, gather=True):
+        if name in self._overrides:
+            return self._overrides[name]
+        if cache and name in self._fields:
+            return self._fields[name]
+        t = self._field_device(name)
+        if gather and self._world > 1:
+            t = gather_x(t, self._nx, self._rank, self._world, dim=0)
+        arr = t.cpu().numpy()
+        if cache:
+            self._fields[name] = arr
+        return arr
+
+    # ------------------------------------------------------------------ 3-D properties
+    @property
+    def fill_factor(self):
+        """classes.py:571-769"""
+        return self._field('fill_factor')
+
+    @property
+    def areas(self):
+        """classes.py:771-784"""
+        return self._field('areas')
+
+    @property
+    def ts(self):
+        """Launch time of the material in each cell [s] (classes.py:838-859)"""
+        if 'travel' in self._overrides:
+            return self.time - self._overrides['travel']
+        return self.time - self._field('travel')
+
+    @ts.setter
+    def ts(self, new_ts):
+        self._overrides['travel'] = new_ts
+        self._invalidate()
+
+    @property
+    def chi_xyz(self):
+        """Burst factor per cell (classes.py:861-870)"""
+        return self._field('chi', cache=False)
+
+    @property
+    def number_density(self):
+        """cm^-3, including the burst factor (classes.py:872-899)"""
+        return self._field('nd_base') * self.chi_xyz
+
+    @property
+    def mass_density(self):
+        """g cm^-3 (classes.py:901-908)"""
+        av_m_particle = self.params['properties']['mu'] * hm.atomic_mass("H")
+        return av_m_particle * 1e3 * self.number_density
+
+    @property
+    def ion_fraction(self):
+        """classes.py:910-936"""
+        return self._field('xi')
+
+    @ion_fraction.setter
+    def ion_fraction(self, new_xis):
+        self._overrides['xi'] = new_xis
+        self._invalidate()
+
+    @property
+    def temperature(self):
+        """K (classes.py:942-969)"""
+        return self._field('temp')
+
+    @temperature.setter
+    def temperature(self, new_ts):
+        self._overrides['temp'] = new_ts
+        self._invalidate()
+
+    @property
+    def pressure(self):
+        """Barye (classes.py:1002-1007)"""
+        return self.number_density * self.temperature * con.k * 1e7
+
+    @property
+    def vel(self):
+        """(vx, v_los, vz) in km/s (classes.py:1009-1095)"""
+        if 'vel' in self._overrides:
+            return self._overrides['vel']
+        return self._field('vx'), self._field('vlos'), self._field('vz')
+
+    @vel.setter
+    def vel(self, new_vs):
+        self._overrides['vel'] = new_vs
+        self._invalidate()
+
+    def _invalidate(self):
+        self._dev = None
+        self._cont = None
+        self._line = None
+        self._fields.clear()
+
+    # ------------------------------------------------------------------ line-of-sight passes
+    def _continuum_struct(self):
+        ct = _cabi.Continuum()
+        ct.em_scale = float(self._csize * con.au / con.parsec)
+        ct.tau_scale = float(0.018 * (self._csize * con.au * 1e2))
+        ct.t_exponent = -1.5 if self._params['power_laws']['q_T'] == 0. else -1.35
+        return ct
+
+    def _ff_coeff(self, freqs):
+        """tau_ff(nu) = coeff(nu) * K with K the frequency-independent ray sum
+        (classes.py:1388-1399, :1421-1429)."""
+        freqs = np.asarray(freqs, dtype=np.float64)
+        if self._params['power_laws']['q_T'] == 0.:
+            g = hm.gff(freqs, self._params['properties']['T_0'])
+            return freqs ** -2. * g
+        return 11.95 * freqs ** -0.1 * freqs ** -2.
+
+    def _pixel_solid_angle(self):
+        return float(np.arctan((self._csize * con.au) /
+                               (self._params["target"]["dist"] * con.parsec)) ** 2.)
+
+    def _pass(self, line=None, freqs=None, contsub=True, want_tau=True, want_flux=True):
+        """One fused line-of-sight pass over the packed state; caches the continuum sums
+        of the current epoch and the last line cube."""
+        torch = _torch()
+        lib = _cabi.load()
+        d = self._ensure_filled()
+        dev = d["device"]
+        nxs, nz = self._x_hi - self._x_lo, self._nz
+        key_c = (float(self._time), len(self._ejections))
+        if line is None:
+            if self._cont is not None and self._cont["key"] == key_c:
+                return self._cont
+        else:
+            key_l = key_c + (line, np.asarray(freqs, np.float64).tobytes(), bool(contsub))
+            if self._line is not None and self._line["key"] == key_l and \
+                    (not want_tau or self._line["tau"] is not None) and \
+                    (not want_flux or self._line["flux"] is not None):
+                return self._line
+        npix = nxs * nz
+        with torch.cuda.device(dev):
+            em = torch.empty(npix, dtype=torch.float64, device=dev)
+            kff = torch.empty(npix, dtype=torch.float64, device=dev)
+            tsum = torch.empty(npix, dtype=torch.float64, device=dev)
+            cnt = torch.empty(npix, dtype=torch.int32, device=dev)
+            ep = self._epoch_struct()
+            ct = self._continuum_struct()
+            tau = flux = None
+            if line is None:
+                st = lib.rjp_integrate(d["model"], ep, ct, d["cells"].data_ptr(),
+                                       em.data_ptr(), kff.data_ptr(), tsum.data_ptr(),
+                                       cnt.data_ptr(), None, None, 0, 1, None, None,
+                                       self._stream())
+            else:
+                ln, chans, keep = self._line_structs(line, freqs, dev)
+                nch = len(freqs)
+                if want_tau:
+                    tau = torch.empty((nch, nxs, nz), dtype=torch.float64, device=dev)
+                if want_flux:
+                    flux = torch.empty((nch, nxs, nz), dtype=torch.float64, device=dev)
+                st = lib.rjp_integrate(d["model"], ep, ct, d["cells"].data_ptr(),
+                                       em.data_ptr(), kff.data_ptr(), tsum.data_ptr(),
+                                       cnt.data_ptr(), ln, chans, nch, 1 if contsub else 0,
+                                       tau.data_ptr() if want_tau else None,
+                                       flux.data_ptr() if want_flux else None,
+                                       self._stream())
+                del keep
+            _cabi.check(st, "rjp_integrate")
+        self._cont = {"key": key_c, "em": em, "kff": kff, "tsum": tsum, "cnt": cnt}
+        if line is None:
+            return self._cont
+        self._line = {"key": key_l, "tau": tau, "flux": flux}
+        return self._line
+
+    def _line_structs(self, line, freqs, dev):
+        """Host scalars of the LTE line opacity (classes.py:1159-1169; rrls.py)."""
+        torch = _torch()
+        element, n, dn = hm.rrl_parser(line)
+        freqs = np.asarray(freqs, dtype=np.float64)
+        nu0 = hm.rrl_nu_0(element, n, dn)
+        m_atom = hm.atomic_mass(element)
+        ln = _cabi.Line()
+        ln.nu0 = float(nu0)
+        ln.dopp = float(1000. / con.c)
+        ln.width_g = float(np.sqrt(2. * con.k / (m_atom * con.c ** 2.)))
+        ln.stark = float(hm.deltanu_l(1.0, n, dn) / 2.)
+        z = hm.z_number(element)
+        ln.kappa0 = float(1.0991132675738456e-17 * n ** 2. * hm.f_n1n2(n, dn) *
+                          hm.ni_from_ne(1.0, element) * (self._csize * con.au * 1e2) /
+                          np.sqrt(np.pi))
+        ln.en_over_k = float(z ** 2. * hm.energy_n(n, element) / hm.k_cgs)
+        ln.h_over_k = float(hm.h_cgs / hm.k_cgs)
+        ln.v_lsr = float(self._params["target"]["v_lsr"])
+        omega_jy = self._pixel_solid_angle() / 1e-26
+        host = np.stack([
+            freqs - nu0,
+            freqs,
+            self._ff_coeff(freqs),
+            2. * freqs ** 2. * con.k / con.c ** 2. * omega_jy,
+            2. * con.h * 1e7 * freqs ** 3. / (con.c * 1e2) ** 2. * (1e-7 * 1e4) * omega_jy,
+        ])
+        devarr = torch.from_numpy(np.ascontiguousarray(host)).to(dev)
+        ch = _cabi.Channels()
+        base, step = devarr.data_ptr(), freqs.size * 8
+        ch.dnu, ch.nu, ch.cff, ch.aff, ch.bnu = (base, base + step, base + 2 * step,
+                                                 base + 3 * step, base + 4 * step)
+        return ln, ch, devarr
+
+    def _host_image(self, t, lead=None):
+        """Device tile(s) -> full host numpy array, all-gathering x-slabs if sharded."""
+        nxs, nz = self._x_hi - self._x_lo, self._nz
+        t = t.view(nxs, nz) if lead is None else t.view(lead, nxs, nz)
+        if self._world > 1:
+            t = gather_x(t, self._nx, self._rank, self._world, dim=0 if lead is None else 1)
+        return _to_host(t)
+
+    def _continuum_images(self, freqs, want):
+        """K5 for a list of frequencies; `want` in ('tau', 'intensity', 'flux')."""
+        torch = _torch()
+        lib = _cabi.load()
+        c = self._pass()
+        dev = c["em"].device
+        freqs = np.atleast_1d(np.asarray(freqs, dtype=np.float64))
+        nf = freqs.size
+        npix = c["em"].numel()
+        coeff = torch.from_numpy(np.stack([self._ff_coeff(freqs),
+                                           2. * freqs ** 2. * con.k / con.c ** 2.])).to(dev)
+        with torch.cuda.device(dev):
+            out = torch.empty((nf, npix), dtype=torch.float64, device=dev)
+            ptrs = {k: (out.data_ptr() if k == want else None)
+                    for k in ('tau', 'intensity', 'flux')}
+            st = lib.rjp_continuum_images(c["kff"].data_ptr(), c["tsum"].data_ptr(),
+                                          c["cnt"].data_ptr(), npix, coeff.data_ptr(),
+                                          coeff.data_ptr() + nf * 8,
+                                          self._pixel_solid_angle() / 1e-26, nf,
+                                          ptrs['tau'], ptrs['intensity'], ptrs['flux'],
+                                          self._stream())
+            _cabi.check(st, "rjp_continuum_images")
+        return self._host_image(out, lead=nf)
+
+    # ------------------------------------------------------------------ public RT methods
+    def emission_measure(self, savefits=False):
+        """Emission measure viewed along the y-axis [pc cm^-6] (classes.py:1101-1128)"""
+        ems = self._host_image(self._pass()["em"])
+        if savefits:
+            self.save_fits(reorder_axes(ems, ra_axis=0, dec_axis=1), savefits, 'em')
+        return ems
+
+    def optical_depth_ff(self, freq, savefits=False, collapse=True):
+        """Free-free optical depth along the y-axis (classes.py:1353-1447)"""
+        scalar = np.isscalar(freq)
+        if not collapse:
+            tff = self._cellwise_tau_ff(np.atleast_1d(freq))
+            return tff[0] if scalar else tff
+        tff = self._continuum_images(freq, 'tau')
+        if scalar:
+            tff = tff[0]
+        if savefits:
+            self._save_image(tff, savefits, 'tau', freq, scalar)
+        return tff
+
+    def intensity_ff(self, freq, savefits=False):
+        """Intensity along the y-axis [W m^-2 Hz^-1 sr^-1] (classes.py:1449-1496)"""
+        scalar = np.isscalar(freq)
+        ints = self._continuum_images(freq, 'intensity')
+        if scalar:
+            ints = ints[0]
+        if savefits:
+            self._save_image(ints, savefits, 'intensity', freq, scalar)
+        return ints
+
+    def flux_ff(self, freq, savefits=False):
+        """Flux [Jy/pixel] (classes.py:1498-1541)"""
+        scalar = np.isscalar(freq)
+        fluxes = self._continuum_images(freq, 'flux')
+        if scalar:
+            fluxes = fluxes[0]
+        if savefits:
+            self._save_image(fluxes, savefits, 'flux', freq, scalar)
+        return fluxes
+
+    def optical_depth_rrl(self, rrl, freq, lte=True, savefits=False, collapse=True):
+        """RRL optical depth along the y-axis (classes.py:1130-1229)"""
+        scalar = np.isscalar(freq)
+        freqs = np.atleast_1d(np.asarray(freq, dtype=np.float64))
+        if not collapse:
+            raise NotImplementedError("collapse=False (per-cell RRL optical depths) is not "
+                                      "provided by the CUDA path")
+        res = self._pass(rrl, freqs, contsub=self._line_contsub_hint(), want_tau=True,
+                         want_flux=True)
+        tau = self._host_image(res["tau"], lead=freqs.size)
+        if scalar:
+            tau = tau[0]
+        if savefits:
+            self._save_image(tau, savefits, 'tau', freq, scalar)
+        return tau
+
+    def _line_contsub_hint(self):
+        # Pipeline asks for tau then for flux with contsub=False (classes.py:2437-2453):
+        # computing that flux cube in the same pass avoids a second sweep.
+        return False
+
+    def intensity_rrl(self, rrl, freq, lte=True, savefits=False):
+        """Line intensity [W m^-2 Hz^-1 sr^-1] (classes.py:1231-1290)"""
+        if not lte:
+            raise ValueError("Non-LTE RRL calculations not yet supported")
+        scalar = np.isscalar(freq)
+        freqs = np.atleast_1d(np.asarray(freq, dtype=np.float64))
+        res = self._pass(rrl, freqs, contsub=True, want_tau=True, want_flux=True)
+        ints = self._host_image(res["flux"], lead=freqs.size) * \
+            (1e-26 / self._pixel_solid_angle())
+        if scalar:
+            ints = ints[0]
+        if savefits:
+            self._save_image(ints, savefits, 'intensity', freq, scalar)
+        return ints
+
+    def flux_rrl(self, rrl, freq, lte=True, contsub=True, savefits=False):
+        """RRL flux [Jy/pixel]; contsub=False adds the continuum (classes.py:1292-1351)"""
+        if not lte:
+            raise ValueError("Non-LTE RRL calculations not yet supported")
+        scalar = np.isscalar(freq)
+        freqs = np.atleast_1d(np.asarray(freq, dtype=np.float64))
+        res = self._pass(rrl, freqs, contsub=contsub, want_tau=True, want_flux=True)
+        fluxes = self._host_image(res["flux"], lead=freqs.size)
+        if scalar:
+            fluxes = fluxes[0]
+        if savefits:
+            self._save_image(fluxes, savefits, 'flux', freq, scalar)
+        return fluxes
+
+    def _cellwise_tau_ff(self, freqs):
+        """collapse=False branch of optical_depth_ff (classes.py:1383, :1395-1397): the
+        un-summed 3-D optical depths, composed on the host from the fp64 field planes
+        (never used by Pipeline; not a hot path)."""
+        n_es = self.number_density * self.ion_fraction
+        t = self.temperature
+        path = self._csize * con.au * 1e2 * (self.fill_factor / self.areas)
+        out = np.empty((len(freqs),) + n_es.shape)
+        with np.errstate(all='ignore'):
+            for i, nu in enumerate(freqs):
+                if self._params['power_laws']['q_T'] == 0.:
+                    g = hm.gff(float(nu), self._params['properties']['T_0'])
+                else:
+                    g = 11.95 * t ** 0.15 * nu ** -0.1
+                out[i] = 0.018 * t ** -1.5 * nu ** -2. * n_es ** 2. * path * g
+        return out
+
+    # ------------------------------------------------------------------ products
+    def _save_image(self, data, filename, image_type, freq, scalar):
+        if scalar:
+            self.save_fits(reorder_axes(data, ra_axis=0, dec_axis=1), filename, image_type,
+                           freq)
+        else:
+            self.save_fits(reorder_axes(data, ra_axis=1, dec_axis=2, axis3=0,
+                                        axis3_type='freq'), filename, image_type, freq)
+
+    def save_fits(self, data, filename, image_type, freq=None):
+        """Write a FITS image/cube with the reference's header (classes.py:1543-1652)."""
+        from .fitsio import write_model_fits
+        if image_type not in ('flux', 'tau', 'em', 'intensity'):
+            raise ValueError("arg image_type must be one of 'flux', 'tau' or 'em'")
+        write_model_fits(self, data, filename, image_type, freq)
+        return None
+
+    def save(self, filename):
+        """Pickle params / fill factors / areas / time / log (classes.py:1704-1713)"""
+        filled = self._dev is not None
+        ps = {'params': self._params,
+              'areas': self.areas if filled else None,
+              'ffs': self.fill_factor if filled else None,
+              'time': self.time,
+              'log': self.log}
+        self.log.add_entry("INFO", "Saving physical model to {}".format(filename))
+        with open(filename, "wb") as f:
+            pickle.dump(ps, f)
+        return None
+
+
+def _to_host(t):
+    """Device tensor -> numpy through a pinned staging buffer."""
+    torch = _torch()
+    if t.device.type != "cuda":
+        return t.contiguous().numpy()
+    t = t.contiguous()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
+
+
+def reorder_axes(data, ra_axis, dec_axis, axis3=None, axis4=None, axis3_type=None,
+                 axis4_type=None):
+    """Copy of `data` with axes ordered (..., dec, ra) as FITS wants them
+    (miscellaneous/functions.py:236-301)."""
+    cur = {'ra': ra_axis, 'dec': dec_axis}
+    req = {'ra': 1, 'dec': 0}
+    if axis3 is not None:
+        cur[axis3_type] = axis3
+        req = {k: v + 1 for k, v in req.items()}
+        req[axis3_type] = 0
+        if axis4 is not None:
+            cur[axis4_type] = axis4
+            req = {k: v + 1 for k, v in req.items()}
+            req[axis4_type] = 0
+    order = [None] * len(req)
+    for k, pos in req.items():
+        order[pos] = cur[k]
+    return np.ascontiguousarray(np.transpose(np.asarray(data), order))
+
+
+def check_model_params(params):
+    """Structural validation of a model parameter dict; returns an exception instance
+    (or None) like miscellaneous/functions.py:127-190 does."""
+    if not isinstance(params, dict):
+        return TypeError("model params must be dict")
+    need = {'target': ('name', 'ra', 'dec', 'epoch', 'dist', 'v_lsr', 'M_star', 'R_1', 'R_2'),
+            'grid': ('n_x', 'n_y', 'n_z', 'l_z', 'c_size'),
+            'geometry': ('epsilon', 'opang', 'w_0', 'r_0', 'inc', 'pa', 'rotation'),
+            'power_laws': ('q_v', 'q_T', 'q_x', 'q^d_n', 'q^d_T', 'q^d_v', 'q^d_x'),
+            'properties': ('v_0', 'x_0', 'T_0', 'mu', 'mlr_bj', 'mlr_rj'),
+            'ejection': ('t_0', 'hl', 'chi', 'which')}
+    for section, keys in need.items():
+        if section not in params:
+            return KeyError("{} keyword not found in params dict".format(section))
+        for key in keys:
+            if key not in params[section]:
+                return KeyError("{} keyword not found in {} section of params "
+                                "dict".format(key, section))
+    n = len(params['ejection']['t_0'])
+    for key in ('hl', 'chi', 'which'):
+        if len(params['ejection'][key]) != n:
+            return ValueError("ejection arrays must have equal lengths")
+    return None
