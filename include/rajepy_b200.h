@@ -41,13 +41,15 @@ enum {
 
 /* Per-cell packed state written by rjp_fill_grid and streamed (once) by
  * rjp_integrate: 16 bytes = the algorithmic bytes per cell of SURVEY.md 8(d).
- *   w0: float  n_e0 = n_base * x  [cm^-3] without burst factor; sign bit = red jet (r < 0)
- *   w1: float  T [K];                                           sign bit = half-filled cell
- *   w2: int32  (v_los - v_lsr) / v_scale   (INT32_MIN = NaN velocity)
- *   w3: int32  travel time / t_scale       (seconds from the jet base to the cell)
- * An all-zero cell is outside the jet.  w0 == 0 (ignoring sign): density invalid;
- * w1 == 0 or NaN (ignoring sign): temperature invalid (classes.py:891-897, :963-967). */
-typedef struct { uint32_t w0, w1; int32_t w2, w3; } rjp_cell;
+ *   ne0 : n_base * x [cm^-3] = electron density WITHOUT the burst factor chi(t)
+ *         (classes.py:889-897 times :928-934); 0 = density invalid (NaN in the reference)
+ *   temp: T [K] (classes.py:957-967); sign bit set = half-filled cell (ff = 0.5);
+ *         |temp| == 0 = temperature invalid
+ * An all-zero cell is outside the jet.  Everything else the integrators need per cell
+ * (jet side, travel time -> burst factor, line-of-sight velocity) is an analytic
+ * function of the cell indices and is recomputed in fp64 for the few per cent of cells
+ * that are inside the jet, so the state carries full double precision in 16 bytes. */
+typedef struct { double ne0; double temp; } rjp_cell;
 
 /* Everything the grid fill needs (host scalars derived as JetModel.__init__ does,
  * classes.py:168-242; angles as maths/geometry.py:243-247). */
@@ -75,8 +77,8 @@ typedef struct {
   double hyp_c2;             /* Gamma(b+1) Gamma(a-b) / Gamma(a)                    */
   int32_t hyp_degenerate;    /* 1: b-a (near-)integer -> series only                */
   int32_t reserved0;
-  double t_scale;            /* seconds per count of rjp_cell.w3                    */
-  double v_scale;            /* km/s per count of rjp_cell.w2                       */
+  int32_t need_reff;         /* any of qd_n, qd_x, qd_T != 0                        */
+  int32_t reserved1;
 } rjp_model;
 
 /* One Gaussian ejection burst of one jet (classes.py:399-463). */
@@ -109,7 +111,6 @@ typedef struct {
   double kappa0;        /* 1.0991132675738456e-17 n^2 f (X mu'/m_amu) cs au 100 / sqrt(pi) */
   double en_over_k;     /* Z^2 E_n / k_cgs  [K]  (rrls.py:386)                    */
   double h_over_k;      /* h / k [K s]                                            */
-  double v_lsr;         /* km/s                                                   */
 } rjp_line;
 
 /* Per-channel host-prepared scalars, each a DEVICE array of nchan doubles. */
@@ -138,8 +139,7 @@ int rjp_struct_sizes(int32_t* model, int32_t* epoch, int32_t* continuum, int32_t
  *                          test is too close to call in device arithmetic; *n_ties
  *                          (device) receives the number found (may exceed capacity:
  *                          then re-run with a larger list)
- *   status [4] int32 device: [0] cells whose travel time overflowed t_scale,
- *                          [1] cells whose velocity overflowed v_scale          */
+ *   status [4] int32 device: reserved (zero)                                    */
 int rjp_fill_grid(const rjp_model* m_host, uint8_t* nverts, rjp_cell* cells,
                   int32_t* ties, int32_t tie_capacity, int32_t* n_ties,
                   int32_t* status, void* stream);

@@ -28,7 +28,7 @@ class Model(C.Structure):
             "n0", "x0", "T0", "v0", "f_rb", "gm_over_au", "rot_sign", "v_lsr", "au_m",
             "year_s", "au_cm", "hyp_b", "hyp_c1", "hyp_c2")] +
         [("hyp_degenerate", C.c_int32), ("reserved0", C.c_int32),
-         ("t_scale", C.c_double), ("v_scale", C.c_double)])
+         ("need_reff", C.c_int32), ("reserved1", C.c_int32)])
 
 
 class Burst(C.Structure):
@@ -47,7 +47,7 @@ class Continuum(C.Structure):
 
 class Line(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("nu0", "dopp", "width_g", "stark", "kappa0",
-                                          "en_over_k", "h_over_k", "v_lsr")]
+                                          "en_over_k", "h_over_k")]
 
 
 class Channels(C.Structure):

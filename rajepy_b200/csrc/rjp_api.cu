@@ -36,7 +36,7 @@ static int check_launch(int st) {
 
 static bool model_ok(const rjp_model* m) {
   return m && m->nx > 0 && m->ny > 0 && m->nz > 0 && m->x_lo >= 0 && m->x_hi <= m->nx &&
-         m->x_lo < m->x_hi && m->cs > 0.0 && m->t_scale > 0.0 && m->v_scale > 0.0;
+         m->x_lo < m->x_hi && m->cs > 0.0;
 }
 
 extern "C" const char* rjp_strerror(int status) {

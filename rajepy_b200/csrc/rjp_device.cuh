@@ -129,21 +129,15 @@ __device__ inline double hyp2f1_bp1(const rjp_model& m, double z) {
 }
 
 // ---------------------------------------------------------------- per-cell physics
-struct CellProps {
-  double r, w, phi, reff;      // centroid jet coordinates (classes.py:515-557)
-  double travel;               // s (classes.py:852 / geometry.py:121-178)
-  double nd, xi, temp;         // unmasked-by-ff values with the 0/inf -> NaN rule
-  double vx, vlos_rel, vz;     // km/s after rotation to the observer; vlos_rel excludes v_lsr
-};
-
-// maths/geometry.py:150-173, SI units.
+// maths/geometry.py:150-173, SI units.  `reff_si` is only read when q^d_v != 0.
 __device__ inline double travel_indef(const rjp_model& m, double r_si, double w_si) {
   const double W0 = m.w0 * m.au_m, R0 = m.r0 * m.au_m, MR0 = m.mr0 * m.au_m;
-  const double R1 = m.R1 * m.au_m, R2 = m.R2 * m.au_m, V0 = m.v0 * 1e3;
+  const double V0 = m.v0 * 1e3;
   const double cst = powq(MR0, m.q_v) / (V0 * (1.0 - m.q_v + m.eps * m.qd_v));
   const double rad = r_si + MR0 - R0;
   const double p1 = powq(rad, 1.0 - m.q_v);
   if (m.qd_v == 0.0) return cst * p1;
+  const double R1 = m.R1 * m.au_m, R2 = m.R2 * m.au_m;
   // r_eff with |r| in SI (geometry.py:157)
   const double rhos = (MR0 != 0.0) ? (fabs(r_si) + MR0 - R0) / MR0 : fabs(r_si) / R0;
   const double reff = R1 + ((R2 - R1) * w_si) / (W0 * pow(rhos, m.eps));
@@ -164,99 +158,91 @@ __device__ __forceinline__ double clean(double v) {  // 0 -> NaN, +-inf -> NaN
   return (v == 0.0 || isinf(v)) ? dnan() : v;
 }
 
-__device__ inline CellProps cell_props(const rjp_model& m, int ix, int iy, int iz,
-                                       bool want_phi) {
-  CellProps o;
+// Centroid of cell (ix, iy, iz) in jet coordinates: corner + cs/2 (classes.py:521-523).
+__device__ __forceinline__ Rw centroid_rw(const rjp_model& m, int ix, int iy, int iz) {
   const double h = m.cs / 2.0;
-  const double xc = __dadd_rn(corner(m.cs, ix, m.nx), h);
-  const double yc = __dadd_rn(corner(m.cs, iy, m.ny), h);
-  const double zc = __dadd_rn(corner(m.cs, iz, m.nz), h);
-  Rw g = xyz_to_rw(m, xc, yc, zc);
-  o.r = g.r;
-  o.w = g.w;
-  const double q = g.y2 / g.w;  // sin(phi); NaN on the axis like arcsin(0/0)
-  if (want_phi) {
-    double p = asin(q);
-    o.phi = (g.x1 < 0.0) ? (CUDART_PI - p) : p;
-  } else {
-    o.phi = 0.0;
-  }
+  return xyz_to_rw(m, __dadd_rn(corner(m.cs, ix, m.nx), h),
+                   __dadd_rn(corner(m.cs, iy, m.ny), h),
+                   __dadd_rn(corner(m.cs, iz, m.nz), h));
+}
+
+// |r| with the jet-base shift of classes.py:848-850 (= :884-886, :922-924, :1050-1052).
+__device__ __forceinline__ double r_shifted(const rjp_model& m, double ar) {
+  const double h = m.cs / 2.0;
+  return (ar < m.r0 && (ar + h) >= m.r0) ? (m.r0 + ar + h) / 2.0 : ar;
+}
+
+// Travel time from the jet base to the cell [s]: classes.py:852 / geometry.py:177-178.
+__device__ __forceinline__ double travel_time(const rjp_model& m, const Rw& g) {
+  const double rt = r_shifted(m, fabs(g.r));
+  const double F1 = travel_indef(m, rt * m.au_m, g.w * m.au_m);
+  const double F0 = travel_indef(m, m.r0 * m.au_m, g.w * m.au_m);
+  return (F1 - F0) / m.year_s * m.year_s;
+}
+
+// r_eff at the centroid: geometry.py:336 with |r| (classes.py:549-555).
+__device__ __forceinline__ double reff_of(const rjp_model& m, const Rw& g, double rho_c_eps) {
+  return m.R1 + ((m.R2 - m.R1) * g.w) / (m.w0 * rho_c_eps);
+}
+
+struct Velocity { double vx, vlos_rel, vz; };  // km/s, observer frame; vlos excludes v_lsr
+
+// classes.py:1056-1093, physics.py:90, geometry.py:249-258 ('xy', 90 - inc, -pa).
+__device__ inline Velocity velocity_of(const rjp_model& m, const Rw& g) {
   const double ar = fabs(g.r);
   const double rho_c = rho_of(m, ar);
-  // geometry.py:336 with |r| (classes.py:549-555)
-  o.reff = m.R1 + ((m.R2 - m.R1) * g.w) / (m.w0 * pow(rho_c, m.eps));
-  // base shift: classes.py:848-850
-  double rt = ar;
-  if (ar < m.r0 && (ar + h) >= m.r0) rt = (m.r0 + ar + h) / 2.0;
-  const double rho_t = rho_of(m, rt);
-  const double x_re = o.reff / m.R1;
-  // classes.py:889-897
+  const double rce = pow(rho_c, m.eps);
+  const double reff = reff_of(m, g, rce);
+  const double rho_t = rho_of(m, r_shifted(m, ar));
+  double vz = clean(m.v0 * powq(rho_t, m.q_v) * powq(reff / m.R1, m.qd_v));
+  const double sgn = (g.r > 0.0) ? 1.0 : ((g.r < 0.0) ? -1.0 : 0.0);
+  vz *= sgn;
+  const double vrot = sqrt(m.gm_over_au / reff) * (1.0 / rce) / 1e3;
+  const double q = g.y2 / g.w;  // sin(phi); NaN on the axis like arcsin(0/0)
+  const double vxj = -vrot * q * m.rot_sign;
+  const double vyj = vrot * (g.x1 / g.w) * m.rot_sign;
+  const double y1 = m.cva * vyj - m.sva * vz;
+  const double z1 = m.sva * vyj + m.cva * vz;
+  Velocity v;
+  v.vx = m.cvb * vxj + m.svb * z1;
+  v.vlos_rel = y1;
+  v.vz = m.cvb * z1 - m.svb * vxj;
+  return v;
+}
+
+struct Laws { double nd, xi, temp, reff; };  // with the 0/inf -> NaN rule, not ff-masked
+
+// classes.py:889-897 (n), :928-934 (x), :957-967 (T, incl. the cm-vs-au quirk).
+__device__ inline Laws laws_of(const rjp_model& m, const Rw& g, bool force_reff) {
+  Laws o;
+  const double ar = fabs(g.r);
+  double x_re = 1.0;
+  o.reff = dnan();
+  if (m.need_reff || force_reff) {
+    o.reff = reff_of(m, g, pow(rho_of(m, ar), m.eps));
+    x_re = o.reff / m.R1;
+  }
+  const double rho_t = rho_of(m, r_shifted(m, ar));
   double nd = clean(m.n0 * powq(rho_t, m.q_n) * powq(x_re, m.qd_n));
   if (g.r < 0.0) nd *= m.f_rb;
   o.nd = isinf(nd) ? dnan() : nd;
-  // classes.py:928-934
   o.xi = clean(m.x0 * powq(rho_t, m.q_x) * powq(x_re, m.qd_x));
-  // classes.py:957-967: |r| in cm compared with r_0 in au (reference quirk, kept)
-  double rT = ar * m.au_cm;
+  const double h = m.cs / 2.0;
+  double rT = ar * m.au_cm;  // |r| in cm compared with r_0 in au (reference quirk, kept)
   if (rT < m.r0 && (rT + h) >= m.r0) rT = (m.r0 + rT + h) / 2.0;
   o.temp = clean(m.T0 * powq(rho_of(m, rT), m.q_T) * powq(x_re, m.qd_T));
-  // classes.py:1056-1093, physics.py:90
-  double vz = clean(m.v0 * powq(rho_t, m.q_v) * powq(x_re, m.qd_v));
-  const double sgn = (g.r > 0.0) ? 1.0 : ((g.r < 0.0) ? -1.0 : 0.0);
-  vz *= sgn;
-  const double vrot = sqrt(m.gm_over_au / o.reff) * pow(rho_c, -m.eps) / 1e3;
-  const double vxj = -vrot * q * m.rot_sign;
-  const double vyj = vrot * (g.x1 / g.w) * m.rot_sign;
-  // xyz_rotate(vx, vy, vz, 90 - inc, -pa, 'xy'): geometry.py:249-258
-  const double y1 = m.cva * vyj - m.sva * vz;
-  const double z1 = m.sva * vyj + m.cva * vz;
-  o.vx = m.cvb * vxj + m.svb * z1;
-  o.vlos_rel = y1;
-  o.vz = m.cvb * z1 - m.svb * vxj;
-  // classes.py:852: t_rw(r_shifted, w) * year
-  const double F1 = travel_indef(m, rt * m.au_m, g.w * m.au_m);
-  const double F0 = travel_indef(m, m.r0 * m.au_m, g.w * m.au_m);
-  o.travel = (F1 - F0) / m.year_s * m.year_s;
   return o;
 }
 
 // Pack one in-jet cell (nverts > 0) into the 16-byte state.
-__device__ inline rjp_cell pack_cell(const rjp_model& m, const CellProps& p, int nverts,
-                                     int32_t* status) {
+__device__ inline rjp_cell pack_cell(const rjp_model& m, int ix, int iy, int iz, int nverts) {
+  const Rw g = centroid_rw(m, ix, iy, iz);
+  const Laws l = laws_of(m, g, false);
   rjp_cell c;
-  const bool red = p.r < 0.0;
-  const bool half = nverts < 8;
-  double ne0 = p.nd * p.xi;
-  float f0 = 0.f;
-  int32_t tq = 0;
-  if (ne0 == ne0 && !isinf(ne0) && p.travel == p.travel) {
-    f0 = (float)ne0;
-    if (isinf(f0)) f0 = 0.f;
-    double tc = rint(p.travel / m.t_scale);
-    if (fabs(tc) > 2147483000.0) {
-      atomicAdd(&status[0], 1);
-      tc = copysign(2147483000.0, tc);
-    }
-    tq = (int32_t)tc;
-  }
-  float tf = 0.f;
-  if (p.temp == p.temp && p.temp > 0.0) {
-    tf = (float)p.temp;
-    if (isinf(tf)) tf = 0.f;
-  }
-  int32_t vq = INT32_MIN;
-  if (p.vlos_rel == p.vlos_rel) {
-    double vc = rint(p.vlos_rel / m.v_scale);
-    if (fabs(vc) > 2147483000.0) {
-      atomicAdd(&status[1], 1);
-      vc = copysign(2147483000.0, vc);
-    }
-    vq = (int32_t)vc;
-  }
-  c.w0 = __float_as_uint(f0) | (red ? 0x80000000u : 0u);
-  c.w1 = __float_as_uint(tf) | (half ? 0x80000000u : 0u);
-  c.w2 = vq;
-  c.w3 = tq;
+  const double ne0 = l.nd * l.xi;
+  c.ne0 = (ne0 == ne0 && !isinf(ne0) && ne0 > 0.0) ? ne0 : 0.0;
+  double t = (l.temp == l.temp && l.temp > 0.0) ? l.temp : 0.0;
+  c.temp = (nverts < 8) ? -t : t;  // -0.0 keeps the flag when T is invalid
   return c;
 }
 

@@ -23,7 +23,6 @@ fill_grid_kernel(const rjp_model m, uint8_t* __restrict__ nverts,
                  int32_t tie_capacity, int32_t* __restrict__ n_ties,
                  int32_t* __restrict__ status) {
   __shared__ uint8_t s_in[NVERT];
-  const int nxs = m.x_hi - m.x_lo;
   const int tiles_z = (m.nz + TZ - 1) / TZ;
   const int tiles_y = (m.ny + TY - 1) / TY;
   int t = blockIdx.x;
@@ -72,10 +71,9 @@ fill_grid_kernel(const rjp_model m, uint8_t* __restrict__ nverts,
     }
     const size_t idx = ((size_t)(ix - m.x_lo) * m.ny + iy) * m.nz + iz;
     nverts[idx] = (uint8_t)cnt;
-    rjp_cell c = {0u, 0u, 0, 0};
-    if (cnt > 0) c = pack_cell(m, cell_props(m, ix, iy, iz, false), cnt, status);
-    reinterpret_cast<uint4*>(cells)[idx] = make_uint4(c.w0, c.w1, (uint32_t)c.w2,
-                                                       (uint32_t)c.w3);
+    rjp_cell c = {0.0, 0.0};
+    if (cnt > 0) c = pack_cell(m, ix, iy, iz, cnt);
+    reinterpret_cast<double2*>(cells)[idx] = make_double2(c.ne0, c.temp);
   }
 }
 
@@ -92,8 +90,8 @@ __global__ void patch_cells_kernel(const rjp_model m, const int64_t* __restrict_
   const int ix = m.x_lo + (int)(idx / ((int64_t)m.nz * m.ny));
   const int cnt = new_count[i];
   nverts[idx] = (uint8_t)cnt;
-  rjp_cell c = {0u, 0u, 0, 0};
-  if (cnt > 0) c = pack_cell(m, cell_props(m, ix, iy, iz, false), cnt, status);
+  rjp_cell c = {0.0, 0.0};
+  if (cnt > 0) c = pack_cell(m, ix, iy, iz, cnt);
   cells[idx] = c;
 }
 
@@ -117,22 +115,26 @@ cell_field_kernel(const rjp_model m, const rjp_epoch ep, const uint8_t* __restri
         const int iz = (int)(idx % m.nz);
         const int iy = (int)((idx / m.nz) % m.ny);
         const int ix = m.x_lo + (int)(idx / ((size_t)m.nz * m.ny));
-        CellProps p = cell_props(m, ix, iy, iz, field == RJP_FIELD_PHI);
+        const Rw g = centroid_rw(m, ix, iy, iz);
         switch (field) {
-          case RJP_FIELD_R: v = p.r; break;
-          case RJP_FIELD_W: v = p.w; break;
-          case RJP_FIELD_PHI: v = p.phi; break;
-          case RJP_FIELD_REFF: v = p.reff; break;
-          case RJP_FIELD_TRAVEL: v = p.travel; break;
-          case RJP_FIELD_ND_BASE: v = p.nd; break;
-          case RJP_FIELD_XI: v = p.xi; break;
-          case RJP_FIELD_TEMP: v = p.temp; break;
-          case RJP_FIELD_VX: v = p.vx; break;
-          case RJP_FIELD_VLOS: v = p.vlos_rel + m.v_lsr; break;
-          case RJP_FIELD_VZ: v = p.vz; break;
+          case RJP_FIELD_R: v = g.r; break;
+          case RJP_FIELD_W: v = g.w; break;
+          case RJP_FIELD_PHI: {  // geometry.py:291-294
+            const double p = asin(g.y2 / g.w);
+            v = (g.x1 < 0.0) ? (CUDART_PI - p) : p;
+            break;
+          }
+          case RJP_FIELD_REFF: v = laws_of(m, g, true).reff; break;
+          case RJP_FIELD_TRAVEL: v = travel_time(m, g); break;
+          case RJP_FIELD_ND_BASE: v = laws_of(m, g, false).nd; break;
+          case RJP_FIELD_XI: v = laws_of(m, g, false).xi; break;
+          case RJP_FIELD_TEMP: v = laws_of(m, g, false).temp; break;
+          case RJP_FIELD_VX: v = velocity_of(m, g).vx; break;
+          case RJP_FIELD_VLOS: v = velocity_of(m, g).vlos_rel + m.v_lsr; break;
+          case RJP_FIELD_VZ: v = velocity_of(m, g).vz; break;
           case RJP_FIELD_CHI: {
-            const double tl = ep.time - p.travel;
-            v = (p.r < 0.0) ? burst_chi(ep.red, ep.n_red, tl)
+            const double tl = ep.time - travel_time(m, g);
+            v = (g.r < 0.0) ? burst_chi(ep.red, ep.n_red, tl)
                             : burst_chi(ep.blue, ep.n_blue, tl);
             break;
           }

@@ -4,7 +4,7 @@
 //
 // Mapping: a CTA owns ZT = 32 adjacent rays (fixed x, 32 consecutive z) over the whole
 // line of sight (y).  Lanes run along z, so every warp-wide load is one contiguous
-// 512-byte row of `uint4` cells; warps stride along y and keep RPW rows in flight each.
+// 512-byte row of 16-byte cells; warps stride along y and keep RPW rows in flight each.
 // Sums are accumulated in fp64 registers per (warp, ray) and reduced across the CTA's
 // warps through shared memory at the end -- no atomics, deterministic order.
 //
@@ -35,11 +35,33 @@ struct LineEntry {   // channel-independent factors of one in-jet cell (rrls.py:
   int pad;
 };
 
-__device__ __forceinline__ uint4 ld_cell(const uint4* p) {
-  uint4 r;  // streamed once: do not keep in L1
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+__device__ __forceinline__ double2 ld_cell(const double2* p) {
+  double2 r;  // streamed once: do not keep in L1
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+               : "=d"(r.x), "=d"(r.y) : "l"(p));
   return r;
+}
+
+__device__ __forceinline__ bool empty_cell(const double2& c) {
+  return c.x == 0.0 && c.y == 0.0;  // (-0.0 == 0.0): nothing to add either way
+}
+
+// Kernel parameters live in the constant bank; the sparse slow paths below are real
+// (non-inlined) functions that take pointers, so each CTA stages the two parameter
+// blocks in shared memory once (1.2 KB) instead of every thread copying them to its
+// local-memory stack.
+struct Params { rjp_model m; rjp_epoch ep; };
+
+__device__ __forceinline__ void stage_params(Params* s_p, const rjp_model& m,
+                                             const rjp_epoch& ep) {
+  const int nm = sizeof(rjp_model) / 4, ne = sizeof(rjp_epoch) / 4;
+  const uint32_t* gm = reinterpret_cast<const uint32_t*>(&m);
+  const uint32_t* ge = reinterpret_cast<const uint32_t*>(&ep);
+  uint32_t* dm = reinterpret_cast<uint32_t*>(&s_p->m);
+  uint32_t* de = reinterpret_cast<uint32_t*>(&s_p->ep);
+  for (int i = threadIdx.x; i < nm; i += blockDim.x) dm[i] = gm[i];
+  for (int i = threadIdx.x; i < ne; i += blockDim.x) de[i] = ge[i];
+  __syncthreads();
 }
 
 struct Decoded {
@@ -47,23 +69,29 @@ struct Decoded {
   double temp;    // K, 0 if invalid
   double ffw;     // 0.5 or 1
   bool ne_ok, t_ok;
+  Rw g;           // centroid jet coordinates
 };
 
-__device__ __forceinline__ Decoded decode(const uint4& c, const rjp_model& m,
-                                          const rjp_epoch& ep) {
+// The burst factor needs the launch time of the cell's material: model time minus the
+// travel time from the jet base (classes.py:845, :866-868), an analytic function of the
+// cell indices that is recomputed here in fp64 (in-jet cells only).
+// Deliberately NOT inlined: it runs for the sparse in-jet cells only, and keeping its
+// pow/exp/2F1 code out of the streaming loops keeps their register footprint small.
+__device__ __noinline__ Decoded decode(const double2& c, const rjp_model& m,
+                                       const rjp_epoch& ep, int ix, int iy, int iz) {
   Decoded d;
-  const float f0 = __uint_as_float(c.x & 0x7fffffffu);
-  const float tf = __uint_as_float(c.y & 0x7fffffffu);
-  d.ffw = (c.y & 0x80000000u) ? 0.5 : 1.0;
-  d.ne_ok = f0 > 0.f;
-  d.t_ok = tf > 0.f;  // false for 0 and NaN
-  d.temp = d.t_ok ? (double)tf : 0.0;
+  d.ffw = signbit(c.y) ? 0.5 : 1.0;
+  d.temp = fabs(c.y);
+  d.t_ok = d.temp > 0.0;
+  d.ne_ok = c.x > 0.0;
   d.ne = 0.0;
+  d.g = centroid_rw(m, ix, iy, iz);
   if (d.ne_ok) {
-    const double tl = ep.time - (double)(int32_t)c.w * m.t_scale;  // classes.py:845
-    const double chi = (c.x & 0x80000000u) ? burst_chi(ep.red, ep.n_red, tl)
-                                           : burst_chi(ep.blue, ep.n_blue, tl);
-    d.ne = (double)f0 * chi;  // classes.py:875, :1375
+    const double tl = ep.time - travel_time(m, d.g);
+    const double chi = (d.g.r < 0.0) ? burst_chi(ep.red, ep.n_red, tl)
+                                     : burst_chi(ep.blue, ep.n_blue, tl);
+    d.ne = c.x * chi;  // classes.py:875, :1375
+    if (!(d.ne == d.ne)) { d.ne = 0.0; d.ne_ok = false; }  // NaN travel time -> NaN density
   }
   return d;
 }
@@ -122,31 +150,34 @@ __device__ __forceinline__ void reduce_and_store(ContAcc a, const rjp_continuum&
 }
 
 // ------------------------------------------------------------------ continuum only
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 integrate_continuum_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
-                           const uint4* __restrict__ cells, double* __restrict__ em,
+                           const double2* __restrict__ cells, double* __restrict__ em,
                            double* __restrict__ kff, double* __restrict__ tsum,
                            int32_t* __restrict__ tcount) {
   __shared__ double s_red[3 * 8 * ZT];
   __shared__ int s_cnt[8 * ZT];
+  __shared__ Params s_p;
+  stage_params(&s_p, m, ep);
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int ztiles = (m.nz + ZT - 1) / ZT;
   const int xl = blockIdx.x / ztiles;
   const int iz = (blockIdx.x % ztiles) * ZT + lane;
   const bool active = iz < m.nz;
-  const uint4* base = cells + (size_t)xl * m.ny * m.nz + (active ? iz : 0);
+  const double2* base = cells + (size_t)xl * m.ny * m.nz + (active ? iz : 0);
+  const int ix = m.x_lo + xl;
   ContAcc a = {0.0, 0.0, 0.0, 0};
   for (int y0 = wrp; y0 < m.ny; y0 += nwarps * RPW) {
-    uint4 c[RPW];
+    double2 c[RPW];
 #pragma unroll
     for (int j = 0; j < RPW; ++j) {
       const int y = y0 + j * nwarps;
-      c[j] = (active && y < m.ny) ? ld_cell(base + (size_t)y * m.nz) : make_uint4(0, 0, 0, 0);
+      c[j] = (active && y < m.ny) ? ld_cell(base + (size_t)y * m.nz) : make_double2(0.0, 0.0);
     }
 #pragma unroll
     for (int j = 0; j < RPW; ++j) {
-      if (((c[j].x | c[j].y) & 0x7fffffffu) == 0u) continue;
-      accumulate(a, decode(c[j], m, ep), ct.t_exponent);
+      if (empty_cell(c[j])) continue;
+      accumulate(a, decode(c[j], s_p.m, s_p.ep, ix, y0 + j * nwarps, iz), ct.t_exponent);
     }
   }
   reduce_and_store(a, ct, s_red, s_cnt, nwarps, em, kff, tsum, tcount,
@@ -154,17 +185,14 @@ integrate_continuum_kernel(const rjp_model m, const rjp_epoch ep, const rjp_cont
 }
 
 // ------------------------------------------------------------------ continuum + line
-__device__ __forceinline__ bool line_valid(const uint4& c) {
-  return __uint_as_float(c.x & 0x7fffffffu) > 0.f && __uint_as_float(c.y & 0x7fffffffu) > 0.f &&
-         (int32_t)c.z != INT32_MIN;
+__device__ __forceinline__ bool line_valid(const double2& c) {
+  return c.x > 0.0 && fabs(c.y) > 0.0;
 }
 
-__device__ __forceinline__ LineEntry make_entry(const uint4& c, const Decoded& d,
-                                                const rjp_model& m, const rjp_line& ln,
-                                                int ray) {
+__device__ __noinline__ LineEntry make_entry(const Decoded& d, const rjp_model& m,
+                                             const rjp_line& ln, int ray) {
   LineEntry e;
-  const double vrel = (double)(int32_t)c.z * m.v_scale;
-  const double vlos = vrel + ln.v_lsr;                       // classes.py:1093
+  const double vlos = velocity_of(m, d.g).vlos_rel + m.v_lsr;  // classes.py:1093
   const double shift = -ln.nu0 * (vlos * ln.dopp);           // nu0_cell - nu0 (physics.py:558)
   const double nu0c = ln.nu0 + shift;
   const double s2 = ln.width_g * sqrt(d.temp) * nu0c;        // sigma*sqrt2 (rrls.py:104-118, :349)
@@ -176,6 +204,9 @@ __device__ __forceinline__ LineEntry make_entry(const uint4& c, const Decoded& d
   // rrls.py:383-389 with n_i = (X mu'/m_amu) n_e, times path length and 1/(sigma sqrt(2 pi))
   e.amp = ln.kappa0 * d.ne * d.ne * d.ffw / (d.temp * sqrt(d.temp)) *
           exp(ln.en_over_k / d.temp) * e.inv_s2;
+  if (!(vlos == vlos) || !d.ne_ok) {  // NaN velocity/density: nansum drops the cell
+    e.amp = 0.0; e.xs = 0.0; e.inv_s2 = 0.0; e.y = 1.0;
+  }
   e.ray = ray;
   e.pad = 0;
   return e;
@@ -197,11 +228,13 @@ __device__ __forceinline__ double line_term(const LineEntry& e, double dn) {
 __global__ void __launch_bounds__(256)
 integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
                       const rjp_line ln, const rjp_channels ch, const int nchan,
-                      const int contsub, const uint4* __restrict__ cells,
+                      const int contsub, const double2* __restrict__ cells,
                       double* __restrict__ em, double* __restrict__ kff,
                       double* __restrict__ tsum, int32_t* __restrict__ tcount,
                       double* __restrict__ tau_rrl, double* __restrict__ flux_rrl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ Params s_p;
+  stage_params(&s_p, m, ep);
   const int nwarps = blockDim.x >> 5;
   double* tau_s = reinterpret_cast<double*>(smem_raw);                 // [nchan][TAU_LD]
   LineEntry* list = reinterpret_cast<LineEntry*>(tau_s + (size_t)nchan * TAU_LD);
@@ -216,23 +249,24 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   const int z0 = (blockIdx.x % ztiles) * ZT;
   const int iz = z0 + lane;
   const bool active = iz < m.nz;
-  const uint4* base = cells + (size_t)xl * m.ny * m.nz + (active ? iz : 0);
+  const double2* base = cells + (size_t)xl * m.ny * m.nz + (active ? iz : 0);
   const int nxs = m.x_hi - m.x_lo;
+  const int ix = m.x_lo + xl;
 
   for (int i = tid; i < nchan * TAU_LD; i += blockDim.x) tau_s[i] = 0.0;
 
   ContAcc a = {0.0, 0.0, 0.0, 0};
   const int chunk = nwarps * RPW;
-  uint4 nxt[RPW];
+  double2 nxt[RPW];
 #pragma unroll
   for (int j = 0; j < RPW; ++j) {
     const int y = wrp + j * nwarps;
-    nxt[j] = (active && y < m.ny) ? ld_cell(base + (size_t)y * m.nz) : make_uint4(0, 0, 0, 0);
+    nxt[j] = (active && y < m.ny) ? ld_cell(base + (size_t)y * m.nz) : make_double2(0.0, 0.0);
   }
   __syncthreads();
 
   for (int yc = 0; yc < m.ny; yc += chunk) {
-    uint4 cur[RPW];
+    double2 cur[RPW];
 #pragma unroll
     for (int j = 0; j < RPW; ++j) cur[j] = nxt[j];
     // prefetch the next chunk: in flight while this chunk's profiles are evaluated
@@ -241,14 +275,15 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
       for (int j = 0; j < RPW; ++j) {
         const int y = yc + chunk + wrp + j * nwarps;
         nxt[j] = (active && y < m.ny) ? ld_cell(base + (size_t)y * m.nz)
-                                      : make_uint4(0, 0, 0, 0);
+                                      : make_double2(0.0, 0.0);
       }
     }
     int mine = 0;
 #pragma unroll
     for (int j = 0; j < RPW; ++j) {
-      if (((cur[j].x | cur[j].y) & 0x7fffffffu) == 0u) continue;
-      accumulate(a, decode(cur[j], m, ep), ct.t_exponent);
+      if (empty_cell(cur[j])) continue;
+      accumulate(a, decode(cur[j], s_p.m, s_p.ep, ix, yc + wrp + j * nwarps, iz),
+                 ct.t_exponent);
       mine += line_valid(cur[j]) ? 1 : 0;
     }
     if (!__syncthreads_or(mine > 0)) continue;  // chunk has no line-emitting cell
@@ -276,7 +311,8 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
       for (int j = 0; j < RPW; ++j) {
         if (!line_valid(cur[j])) continue;
         if (rank >= r0 && rank < r0 + LCAP)
-          list[rank - r0] = make_entry(cur[j], decode(cur[j], m, ep), m, ln, lane);
+          list[rank - r0] = make_entry(
+              decode(cur[j], s_p.m, s_p.ep, ix, yc + wrp + j * nwarps, iz), s_p.m, ln, lane);
         ++rank;
       }
       __syncthreads();
@@ -374,7 +410,7 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
   const int nxs = m->x_hi - m->x_lo;
   const long long ctas = (long long)nxs * ((m->nz + ZT - 1) / ZT);
   if (ctas <= 0 || ctas > 2147483647LL) return RJP_ERR_ARG;
-  const uint4* c4 = reinterpret_cast<const uint4*>(cells);
+  const double2* c4 = reinterpret_cast<const double2*>(cells);
   if (nchan <= 0 || ln == nullptr) {
     integrate_continuum_kernel<<<(unsigned)ctas, 256, 0, stream>>>(*m, *ep, *ct, c4, em, kff,
                                                                   tsum, tcount);

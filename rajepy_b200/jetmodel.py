@@ -420,7 +420,7 @@ class JetModel:
     def _stream(self):
         return _torch().cuda.current_stream(self._device()).cuda_stream
 
-    def _model_struct(self, t_scale, v_scale):
+    def _model_struct(self):
         p = self._params
         g, pl, pr, tg = p["geometry"], p["power_laws"], p["properties"], p["target"]
         m = _cabi.Model()
@@ -457,32 +457,8 @@ class JetModel:
                 m.hyp_degenerate = 0
                 m.hyp_c1 = b / (b - a)
                 m.hyp_c2 = float(gamma(b + 1.) * gamma(a - b) * rgamma(a))
-        m.t_scale, m.v_scale = float(t_scale), float(v_scale)
+        m.need_reff = int(any(pl[k] != 0. for k in ("q^d_n", "q^d_x", "q^d_T")))
         return m
-
-    def _scale_guess(self):
-        """Fixed-point scales of the packed state: 2^31 counts span +-4x a host estimate
-        of the largest travel time / line-of-sight speed inside the grid (the fill reports
-        overflows, in which case the scales are widened and the fill repeated)."""
-        p = self._params
-        g, pl, pr, tg = p["geometry"], p["power_laws"], p["properties"], p["target"]
-        half = 0.5 * self._csize * np.array([self._nx, self._ny, self._nz]) + self._csize
-        r_max = float(np.sqrt(np.sum(half ** 2)))
-        mr0, r0 = g["mod_r_0"], g["r_0"]
-        rad0 = mr0 * con.au
-        rad1 = (r_max + mr0 - r0) * con.au
-        qv = pl["q_v"]
-        cst = rad0 ** qv / (pr["v_0"] * 1e3 * (1. - qv + g["epsilon"] * pl["q^d_v"]))
-        t_est = abs(cst * (abs(rad1) ** (1. - qv) - rad0 ** (1. - qv)))
-        spread = max(tg["R_2"] / tg["R_1"], 1.0) ** abs(pl["q^d_v"])
-        t_est = max(t_est * spread * 2.0, r_max * con.au / (pr["v_0"] * 1e3), 1.0)
-        rho_lo = max((max(r0 - self._csize, 0.) + mr0 - r0) / mr0, 1e-3) if mr0 else 1.0
-        rho_hi = (r_max + mr0 - r0) / mr0 if mr0 else r_max / r0
-        v_ax = abs(pr["v_0"]) * max(rho_lo ** qv, rho_hi ** qv) * spread
-        v_rot = np.sqrt(con.G * tg["M_star"] * hm.MSOL / (tg["R_1"] * con.au)) / 1e3 * \
-            max(rho_lo ** -g["epsilon"], 1.0)
-        v_est = max(v_ax + v_rot, 1.0)
-        return 4.0 * t_est / 2 ** 31, 4.0 * v_est / 2 ** 31
 
     def _epoch_struct(self):
         e = _cabi.Epoch()
@@ -511,30 +487,24 @@ class JetModel:
                                 entry="Calculating cells' fill factors/projected areas")
         with torch.cuda.device(dev):
             nverts = torch.empty(ncell, dtype=torch.uint8, device=dev)
-            cells = torch.empty((ncell, 4), dtype=torch.int32, device=dev)
+            cells = torch.empty((ncell, 2), dtype=torch.float64, device=dev)
             ties = torch.empty((_TIE_CAPACITY, 4), dtype=torch.int32, device=dev)
             counters = torch.zeros(8, dtype=torch.int32, device=dev)  # [0] n_ties, [4:8] status
-            t_scale, v_scale = self._scale_guess()
             tie_cap = _TIE_CAPACITY
-            for attempt in range(6):
+            m = self._model_struct()
+            for attempt in range(3):
                 counters.zero_()
-                m = self._model_struct(t_scale, v_scale)
                 st = lib.rjp_fill_grid(m, nverts.data_ptr(), cells.data_ptr(),
                                        ties.data_ptr(), tie_cap, counters.data_ptr(),
                                        counters.data_ptr() + 16, self._stream())
                 _cabi.check(st, "rjp_fill_grid")
                 c = counters.cpu().numpy()
-                if c[4] > 0:
-                    t_scale *= 64.0
-                elif c[5] > 0:
-                    v_scale *= 64.0
-                elif c[0] > tie_cap:
-                    tie_cap = int(c[0]) + 1024
-                    ties = torch.empty((tie_cap, 4), dtype=torch.int32, device=dev)
-                else:
+                if c[0] <= tie_cap:
                     break
+                tie_cap = int(c[0]) + 1024
+                ties = torch.empty((tie_cap, 4), dtype=torch.int32, device=dev)
             else:
-                raise _cabi.EngineError("grid fill: fixed-point scales did not converge")
+                raise _cabi.EngineError("grid fill: tie list did not converge")
             n_ties = int(c[0])
             self._dev = {"nverts": nverts, "cells": cells, "model": m, "device": dev,
                          "n_ties": n_ties, "n_patched": 0}
@@ -596,8 +566,6 @@ class JetModel:
                                  d["nverts"].data_ptr(), d["cells"].data_ptr(),
                                  status.data_ptr(), self._stream())
         _cabi.check(st, "rjp_patch_cells")
-        if int(status[:2].sum()) > 0:
-            raise _cabi.EngineError("fixed-point overflow while patching cells")
 
     def _adopt_fill_factor(self, ffs):
         """Resume path (classes.py:78-84): take fill factors from a saved model instead
@@ -838,7 +806,6 @@ class JetModel:
                           np.sqrt(np.pi))
         ln.en_over_k = float(z ** 2. * hm.energy_n(n, element) / hm.k_cgs)
         ln.h_over_k = float(hm.h_cgs / hm.k_cgs)
-        ln.v_lsr = float(self._params["target"]["v_lsr"])
         omega_jy = self._pixel_solid_angle() / 1e-26
         host = np.stack([
             freqs - nu0,
