@@ -47,10 +47,15 @@ __device__ __forceinline__ bool empty_cell(const double2& c) {
 }
 
 // Kernel parameters live in the constant bank; the sparse slow paths below are real
-// (non-inlined) functions that take pointers, so each CTA stages the two parameter
-// blocks in shared memory once (1.2 KB) instead of every thread copying them to its
-// local-memory stack.
-struct Params { rjp_model m; rjp_epoch ep; };
+// (non-inlined) functions that take pointers, so each CTA stages the parameter blocks
+// in shared memory once (1.2 KB) instead of every thread copying them to its
+// local-memory stack.  Two derived travel-time constants are added on the way.
+struct Params {
+  rjp_model m;
+  rjp_epoch ep;
+  double tt_cst;   // MR0^q_v / (V0 (1 - q_v + eps q^d_v))          (geometry.py:154)
+  double tt_f0;    // tt_cst * MR0^(1 - q_v): indefinite integral at r_0 when q^d_v = 0
+};
 
 __device__ __forceinline__ void stage_params(Params* s_p, const rjp_model& m,
                                              const rjp_epoch& ep) {
@@ -61,7 +66,34 @@ __device__ __forceinline__ void stage_params(Params* s_p, const rjp_model& m,
   uint32_t* de = reinterpret_cast<uint32_t*>(&s_p->ep);
   for (int i = threadIdx.x; i < nm; i += blockDim.x) dm[i] = gm[i];
   for (int i = threadIdx.x; i < ne; i += blockDim.x) de[i] = ge[i];
+  if (threadIdx.x == 0) {
+    const double MR0 = m.mr0 * m.au_m, V0 = m.v0 * 1e3;
+    const double cst = powq(MR0, m.q_v) / (V0 * (1.0 - m.q_v + m.eps * m.qd_v));
+    s_p->tt_cst = cst;
+    s_p->tt_f0 = cst * powq(MR0, 1.0 - m.q_v);
+  }
   __syncthreads();
+}
+
+// Ray constants of thread (ix, iz): the part of maths/geometry.py:249-255 that does not
+// depend on y.  Same roundings as centroid_rw().
+struct Ray { double x1, z1; };
+
+__device__ __forceinline__ Ray ray_of(const rjp_model& m, int ix, int iz) {
+  const double h = m.cs / 2.0;
+  const double x = __dadd_rn(corner(m.cs, ix, m.nx), h);
+  const double z = __dadd_rn(corner(m.cs, iz, m.nz), h);
+  Ray r;
+  r.x1 = __dadd_rn(__dmul_rn(m.cb, x), __dmul_rn(m.sb, z));
+  r.z1 = __dsub_rn(__dmul_rn(m.cb, z), __dmul_rn(m.sb, x));
+  return r;
+}
+
+// Not inlined: rare paths whose pow / 2F1 code would otherwise bloat the streaming loops.
+__device__ __noinline__ double pow_call(double x, double q) { return pow(x, q); }
+
+__device__ __noinline__ double travel_slow(const Params* P, int ix, int iy, int iz) {
+  return travel_time(P->m, centroid_rw(P->m, ix, iy, iz));
 }
 
 struct Decoded {
@@ -69,27 +101,36 @@ struct Decoded {
   double temp;    // K, 0 if invalid
   double ffw;     // 0.5 or 1
   bool ne_ok, t_ok;
-  Rw g;           // centroid jet coordinates
 };
 
 // The burst factor needs the launch time of the cell's material: model time minus the
 // travel time from the jet base (classes.py:845, :866-868), an analytic function of the
-// cell indices that is recomputed here in fp64 (in-jet cells only).
-// Deliberately NOT inlined: it runs for the sparse in-jet cells only, and keeping its
-// pow/exp/2F1 code out of the streaming loops keeps their register footprint small.
-__device__ __noinline__ Decoded decode(const double2& c, const rjp_model& m,
-                                       const rjp_epoch& ep, int ix, int iy, int iz) {
+// cell indices that is recomputed here in fp64 (in-jet cells only).  With no
+// cross-sectional velocity law (q^d_v = 0, every BASELINE configuration) the travel time
+// is the closed form cst * (rad^(1-q_v) - MR0^(1-q_v)) of the axial coordinate alone.
+__device__ __forceinline__ Decoded decode(const double2& c, const Params& P, const Ray& ray,
+                                          int ix, int iy, int iz) {
+  const rjp_model& m = P.m;
   Decoded d;
   d.ffw = signbit(c.y) ? 0.5 : 1.0;
   d.temp = fabs(c.y);
   d.t_ok = d.temp > 0.0;
   d.ne_ok = c.x > 0.0;
   d.ne = 0.0;
-  d.g = centroid_rw(m, ix, iy, iz);
   if (d.ne_ok) {
-    const double tl = ep.time - travel_time(m, d.g);
-    const double chi = (d.g.r < 0.0) ? burst_chi(ep.red, ep.n_red, tl)
-                                     : burst_chi(ep.blue, ep.n_blue, tl);
+    const double y = __dadd_rn(corner(m.cs, iy, m.ny), m.cs / 2.0);
+    const double r = __dadd_rn(__dmul_rn(m.sa, y), __dmul_rn(m.ca, ray.z1));
+    double travel;
+    if (m.qd_v == 0.0) {
+      const double rad = (r_shifted(m, fabs(r)) + m.mr0 - m.r0) * m.au_m;
+      const double e = 1.0 - m.q_v;
+      travel = P.tt_cst * ((e == 1.0) ? rad : pow_call(rad, e)) - P.tt_f0;
+    } else {
+      travel = travel_slow(&P, ix, iy, iz);
+    }
+    const double tl = P.ep.time - travel;
+    const double chi = (r < 0.0) ? burst_chi(P.ep.red, P.ep.n_red, tl)
+                                 : burst_chi(P.ep.blue, P.ep.n_blue, tl);
     d.ne = c.x * chi;  // classes.py:875, :1375
     if (!(d.ne == d.ne)) { d.ne = 0.0; d.ne_ok = false; }  // NaN travel time -> NaN density
   }
@@ -106,7 +147,8 @@ __device__ __forceinline__ void accumulate(ContAcc& a, const Decoded& d, double 
     a.tsum += d.temp;
     a.cnt += 1;
     if (d.ne_ok) {
-      const double tp = (t_exp == -1.5) ? 1.0 / (d.temp * sqrt(d.temp)) : pow(d.temp, t_exp);
+      const double tp = (t_exp == -1.5) ? 1.0 / (d.temp * sqrt(d.temp))
+                                        : pow_call(d.temp, t_exp);
       a.kff += tp * ne2;
     }
   }
@@ -150,7 +192,7 @@ __device__ __forceinline__ void reduce_and_store(ContAcc a, const rjp_continuum&
 }
 
 // ------------------------------------------------------------------ continuum only
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 integrate_continuum_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
                            const double2* __restrict__ cells, double* __restrict__ em,
                            double* __restrict__ kff, double* __restrict__ tsum,
@@ -166,6 +208,7 @@ integrate_continuum_kernel(const rjp_model m, const rjp_epoch ep, const rjp_cont
   const bool active = iz < m.nz;
   const double2* base = cells + (size_t)xl * m.ny * m.nz + (active ? iz : 0);
   const int ix = m.x_lo + xl;
+  const Ray ray = ray_of(s_p.m, ix, iz);
   ContAcc a = {0.0, 0.0, 0.0, 0};
   for (int y0 = wrp; y0 < m.ny; y0 += nwarps * RPW) {
     double2 c[RPW];
@@ -177,7 +220,7 @@ integrate_continuum_kernel(const rjp_model m, const rjp_epoch ep, const rjp_cont
 #pragma unroll
     for (int j = 0; j < RPW; ++j) {
       if (empty_cell(c[j])) continue;
-      accumulate(a, decode(c[j], s_p.m, s_p.ep, ix, y0 + j * nwarps, iz), ct.t_exponent);
+      accumulate(a, decode(c[j], s_p, ray, ix, y0 + j * nwarps, iz), ct.t_exponent);
     }
   }
   reduce_and_store(a, ct, s_red, s_cnt, nwarps, em, kff, tsum, tcount,
@@ -190,9 +233,10 @@ __device__ __forceinline__ bool line_valid(const double2& c) {
 }
 
 __device__ __noinline__ LineEntry make_entry(const Decoded& d, const rjp_model& m,
-                                             const rjp_line& ln, int ray) {
+                                             const rjp_line& ln, int ix, int iy, int iz,
+                                             int ray) {
   LineEntry e;
-  const double vlos = velocity_of(m, d.g).vlos_rel + m.v_lsr;  // classes.py:1093
+  const double vlos = velocity_of(m, centroid_rw(m, ix, iy, iz)).vlos_rel + m.v_lsr;
   const double shift = -ln.nu0 * (vlos * ln.dopp);           // nu0_cell - nu0 (physics.py:558)
   const double nu0c = ln.nu0 + shift;
   const double s2 = ln.width_g * sqrt(d.temp) * nu0c;        // sigma*sqrt2 (rrls.py:104-118, :349)
@@ -252,6 +296,7 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   const double2* base = cells + (size_t)xl * m.ny * m.nz + (active ? iz : 0);
   const int nxs = m.x_hi - m.x_lo;
   const int ix = m.x_lo + xl;
+  const Ray ray = ray_of(s_p.m, ix, iz);
 
   for (int i = tid; i < nchan * TAU_LD; i += blockDim.x) tau_s[i] = 0.0;
 
@@ -282,8 +327,7 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
 #pragma unroll
     for (int j = 0; j < RPW; ++j) {
       if (empty_cell(cur[j])) continue;
-      accumulate(a, decode(cur[j], s_p.m, s_p.ep, ix, yc + wrp + j * nwarps, iz),
-                 ct.t_exponent);
+      accumulate(a, decode(cur[j], s_p, ray, ix, yc + wrp + j * nwarps, iz), ct.t_exponent);
       mine += line_valid(cur[j]) ? 1 : 0;
     }
     if (!__syncthreads_or(mine > 0)) continue;  // chunk has no line-emitting cell
@@ -311,8 +355,8 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
       for (int j = 0; j < RPW; ++j) {
         if (!line_valid(cur[j])) continue;
         if (rank >= r0 && rank < r0 + LCAP)
-          list[rank - r0] = make_entry(
-              decode(cur[j], s_p.m, s_p.ep, ix, yc + wrp + j * nwarps, iz), s_p.m, ln, lane);
+          list[rank - r0] = make_entry(decode(cur[j], s_p, ray, ix, yc + wrp + j * nwarps, iz),
+                                       s_p.m, ln, ix, yc + wrp + j * nwarps, iz, lane);
         ++rank;
       }
       __syncthreads();

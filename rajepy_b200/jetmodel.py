@@ -29,6 +29,13 @@ from .sharding import gather_x, slab_bounds
 
 _TIE_CAPACITY = 1 << 16
 
+# number of kernel launches issued through the C ABI by this process (bench.py reports it)
+LAUNCHES = {"count": 0}
+
+
+def _launched(n=1):
+    LAUNCHES["count"] += n
+
 
 def _torch():
     import torch
@@ -498,6 +505,7 @@ class JetModel:
                                        ties.data_ptr(), tie_cap, counters.data_ptr(),
                                        counters.data_ptr() + 16, self._stream())
                 _cabi.check(st, "rjp_fill_grid")
+                _launched()
                 c = counters.cpu().numpy()
                 if c[0] <= tie_cap:
                     break
@@ -566,6 +574,7 @@ class JetModel:
                                  d["nverts"].data_ptr(), d["cells"].data_ptr(),
                                  status.data_ptr(), self._stream())
         _cabi.check(st, "rjp_patch_cells")
+        _launched()
 
     def _adopt_fill_factor(self, ffs):
         """Resume path (classes.py:78-84): take fill factors from a saved model instead
@@ -594,6 +603,7 @@ class JetModel:
                                      idx.numel(), d["nverts"].data_ptr(),
                                      d["cells"].data_ptr(), status.data_ptr(), self._stream())
             _cabi.check(st, "rjp_patch_cells")
+        _launched()
         self._fields.clear()
         self._cont = self._line = None
 
@@ -617,6 +627,7 @@ class JetModel:
         st = lib.rjp_cell_field(d["model"], ep, d["nverts"].data_ptr(), _cabi.FIELDS[name],
                                 out.data_ptr(), self._stream())
         _cabi.check(st, "rjp_cell_field")
+        _launched()
         return out.view(self._x_hi - self._x_lo, self._ny, self._nz)
 
     def _field(self, name, cache=True, gather=True):
@@ -782,6 +793,7 @@ class JetModel:
                                        self._stream())
                 del keep
             _cabi.check(st, "rjp_integrate")
+            _launched()
         self._cont = {"key": key_c, "em": em, "kff": kff, "tsum": tsum, "cnt": cnt}
         if line is None:
             return self._cont
@@ -829,8 +841,9 @@ class JetModel:
             t = gather_x(t, self._nx, self._rank, self._world, dim=0 if lead is None else 1)
         return _to_host(t)
 
-    def _continuum_images(self, freqs, want):
-        """K5 for a list of frequencies; `want` in ('tau', 'intensity', 'flux')."""
+    def _continuum_images_device(self, freqs, want):
+        """K5 for a list of frequencies; `want` in ('tau', 'intensity', 'flux').
+        Returns a device tensor (nfreq, nx_slab * nz)."""
         torch = _torch()
         lib = _cabi.load()
         c = self._pass()
@@ -851,7 +864,41 @@ class JetModel:
                                           ptrs['tau'], ptrs['intensity'], ptrs['flux'],
                                           self._stream())
             _cabi.check(st, "rjp_continuum_images")
-        return self._host_image(out, lead=nf)
+            _launched()
+        return out
+
+    def _continuum_images(self, freqs, want):
+        out = self._continuum_images_device(freqs, want)
+        return self._host_image(out, lead=out.shape[0])
+
+    def rt_products(self, cont_freqs=None, line=None, chan_freqs=None, contsub=False,
+                    host=True):
+        """Batched driver for one epoch (what Pipeline.execute asks of the model per run,
+        classes.py:2397-2453, in ONE sweep over the grid): emission measure, continuum
+        tau/flux at `cont_freqs`, and -- if `line` is given -- the RRL tau and flux cubes
+        at `chan_freqs`.  `host=False` keeps the (x-gathered) results on the device."""
+        out = {}
+        if line is not None:
+            res = self._pass(line, np.asarray(chan_freqs, np.float64), contsub=contsub)
+            nch = len(chan_freqs)
+        cont = self._pass()
+        conv = self._host_image if host else self._device_image
+        out["em"] = conv(cont["em"])
+        if cont_freqs is not None:
+            nf = len(np.atleast_1d(cont_freqs))
+            out["tau_ff"] = conv(self._continuum_images_device(cont_freqs, 'tau'), lead=nf)
+            out["flux_ff"] = conv(self._continuum_images_device(cont_freqs, 'flux'), lead=nf)
+        if line is not None:
+            out["tau_rrl"] = conv(res["tau"], lead=nch)
+            out["flux_rrl"] = conv(res["flux"], lead=nch)
+        return out
+
+    def _device_image(self, t, lead=None):
+        nxs, nz = self._x_hi - self._x_lo, self._nz
+        t = t.view(nxs, nz) if lead is None else t.view(lead, nxs, nz)
+        if self._world > 1:
+            t = gather_x(t, self._nx, self._rank, self._world, dim=0 if lead is None else 1)
+        return t
 
     # ------------------------------------------------------------------ public RT methods
     def emission_measure(self, savefits=False):
