@@ -215,6 +215,7 @@ def run_gpu(args):
         e1.record()
         out = jm.rt_products(cont, line, chans, contsub=False, host=False)
         kernel_ms.append((e0, e1))
+        jm.release()
         return out
 
     def e2e_step():
@@ -223,6 +224,7 @@ def run_gpu(args):
         s_ff = jm.flux_ff(cont)
         t_l = jm.optical_depth_rrl(line, chans)
         s_l = jm.flux_rrl(line, chans, contsub=False)
+        jm.release()
         return s_ff.nbytes + t_l.nbytes + s_l.nbytes, float(np.nansum(s_l[len(chans) // 2]))
 
     for _ in range(args.warmup):

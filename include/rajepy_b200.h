@@ -111,6 +111,7 @@ typedef struct {
   double kappa0;        /* 1.0991132675738456e-17 n^2 f (X mu'/m_amu) cs au 100 / sqrt(pi) */
   double en_over_k;     /* Z^2 E_n / k_cgs  [K]  (rrls.py:386)                    */
   double h_over_k;      /* h / k [K s]                                            */
+  double dn_max;        /* max_k |nu_k - nu0| [Hz] over the channels of this call  */
 } rjp_line;
 
 /* Per-channel host-prepared scalars, each a DEVICE array of nchan doubles. */
@@ -139,16 +140,19 @@ int rjp_struct_sizes(int32_t* model, int32_t* epoch, int32_t* continuum, int32_t
  *                          test is too close to call in device arithmetic; *n_ties
  *                          (device) receives the number found (may exceed capacity:
  *                          then re-run with a larger list)
- *   status [4] int32 device: reserved (zero)                                    */
+ *   extents [slab rays][2] int32: per ray (x, z) the half-open y-range [y_lo, y_hi)
+ *                          that contains all of its in-jet cells (y_lo >= y_hi: the ray
+ *                          misses the jet); written here, read by the channel loop    */
 int rjp_fill_grid(const rjp_model* m_host, uint8_t* nverts, rjp_cell* cells,
                   int32_t* ties, int32_t tie_capacity, int32_t* n_ties,
-                  int32_t* status, void* stream);
+                  int32_t* extents, void* stream);
 
 /* Apply host-resolved vertex decisions: for n cells (flat slab indices `cell_idx`,
- * device) set nverts to `new_count` (device, uint8) and recompute the packed state. */
+ * device) set nverts to `new_count` (device, uint8), recompute the packed state and
+ * widen the ray extents where a cell enters the jet. */
 int rjp_patch_cells(const rjp_model* m_host, const int64_t* cell_idx,
                     const uint8_t* new_count, int32_t n, uint8_t* nverts,
-                    rjp_cell* cells, int32_t* status, void* stream);
+                    rjp_cell* cells, int32_t* extents, void* stream);
 
 /* Full-precision 3-D property planes on demand (float64, NaN outside the jet where the
  * reference has NaN), for the JetModel properties the plotting code reads. */
@@ -168,19 +172,23 @@ enum {
 int rjp_cell_field(const rjp_model* m_host, const rjp_epoch* ep_host,
                    const uint8_t* nverts, int32_t field, double* out, void* stream);
 
-/* Fused line-of-sight pass (K3+K4+K5): every cell of the slab is read once.
+/* Line-of-sight pass (K3+K4+K5).  The dense sweep reads every cell of the slab once
+ * (continuum sums); the channel loop walks only the per-ray in-jet extents recorded by the
+ * fill and runs beside the sweep on `stream2` when one is given (NULL: same stream).
  * Replaces emission_measure (classes.py:1101-1128), optical_depth_ff (:1353-1447),
  * the nanmean temperature of intensity_ff (:1471-1473), optical_depth_rrl (:1130-1229)
  * and intensity_rrl/flux_rrl (:1231-1351).
  *   em, kff, tsum [nxs*nz] double, tcount [nxs*nz] int32 (always written)
  *   line/ch may be NULL/nchan = 0 for a continuum-only pass; otherwise
  *   tau_rrl and/or flux_rrl ([nchan][nxs][nz] double) may each be NULL.
- *   contsub: 0 -> flux_rrl includes S_ff (what Pipeline requests, classes.py:2450).  */
+ *   contsub: 0 -> flux_rrl includes S_ff (what Pipeline requests, classes.py:2450).
+ * On return all work is ordered on `stream` (stream2 is joined back).              */
 int rjp_integrate(const rjp_model* m_host, const rjp_epoch* ep_host,
                   const rjp_continuum* cont_host, const rjp_cell* cells,
-                  double* em, double* kff, double* tsum, int32_t* tcount,
-                  const rjp_line* line_host, const rjp_channels* ch_host, int32_t nchan,
-                  int32_t contsub, double* tau_rrl, double* flux_rrl, void* stream);
+                  const int32_t* extents, double* em, double* kff, double* tsum,
+                  int32_t* tcount, const rjp_line* line_host, const rjp_channels* ch_host,
+                  int32_t nchan, int32_t contsub, double* tau_rrl, double* flux_rrl,
+                  void* stream, void* stream2);
 
 /* Continuum epilogue (K5) for nfreq frequencies from one pass' kff/tsum/tcount:
  *   tau[f] = cff[f] * kff;  I[f] = iff[f] * Tmean * (1 - exp(-tau));  S[f] = I * omega_jy

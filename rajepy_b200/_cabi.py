@@ -47,7 +47,7 @@ class Continuum(C.Structure):
 
 class Line(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("nu0", "dopp", "width_g", "stark", "kappa0",
-                                          "en_over_k", "h_over_k")]
+                                          "en_over_k", "h_over_k", "dn_max")]
 
 
 class Channels(C.Structure):
@@ -99,8 +99,8 @@ def load():
     lib.rjp_patch_cells.argtypes = [C.POINTER(Model), vp, vp, i32, vp, vp, vp, vp]
     lib.rjp_cell_field.argtypes = [C.POINTER(Model), C.POINTER(Epoch), vp, i32, vp, vp]
     lib.rjp_integrate.argtypes = [C.POINTER(Model), C.POINTER(Epoch), C.POINTER(Continuum),
-                                  vp, vp, vp, vp, vp, C.POINTER(Line), C.POINTER(Channels),
-                                  i32, i32, vp, vp, vp]
+                                  vp, vp, vp, vp, vp, vp, C.POINTER(Line),
+                                  C.POINTER(Channels), i32, i32, vp, vp, vp, vp]
     lib.rjp_continuum_images.argtypes = [vp, vp, vp, i64, vp, vp, dbl, i32, vp, vp, vp, vp]
     for f in ("rjp_struct_sizes", "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field",
               "rjp_integrate", "rjp_continuum_images"):

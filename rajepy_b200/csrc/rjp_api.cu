@@ -13,9 +13,9 @@ int rjp_launch_patch(const rjp_model*, const int64_t*, const uint8_t*, int32_t, 
 int rjp_launch_field(const rjp_model*, const rjp_epoch*, const uint8_t*, int32_t, double*,
                      cudaStream_t);
 int rjp_launch_integrate(const rjp_model*, const rjp_epoch*, const rjp_continuum*,
-                         const rjp_cell*, double*, double*, double*, int32_t*,
-                         const rjp_line*, const rjp_channels*, int, int, double*, double*,
-                         cudaStream_t);
+                         const rjp_cell*, const int32_t*, double*, double*, double*, int32_t*,
+                         const rjp_line*, const rjp_channels*, int, int, double, double*,
+                         double*, cudaStream_t, cudaStream_t);
 int rjp_launch_continuum_images(const double*, const double*, const int32_t*, int64_t,
                                 const double*, const double*, double, int, double*, double*,
                                 double*, cudaStream_t);
@@ -67,21 +67,21 @@ extern "C" int rjp_struct_sizes(int32_t* model, int32_t* epoch, int32_t* continu
 
 extern "C" int rjp_fill_grid(const rjp_model* m, uint8_t* nverts, rjp_cell* cells,
                              int32_t* ties, int32_t tie_capacity, int32_t* n_ties,
-                             int32_t* status, void* stream) {
-  if (!model_ok(m) || !nverts || !cells || !n_ties || !status || tie_capacity < 0 ||
+                             int32_t* extents, void* stream) {
+  if (!model_ok(m) || !nverts || !cells || !n_ties || !extents || tie_capacity < 0 ||
       (tie_capacity > 0 && !ties))
     return RJP_ERR_ARG;
-  return check_launch(rjp_launch_fill(m, nverts, cells, ties, tie_capacity, n_ties, status,
+  return check_launch(rjp_launch_fill(m, nverts, cells, ties, tie_capacity, n_ties, extents,
                                       (cudaStream_t)stream));
 }
 
 extern "C" int rjp_patch_cells(const rjp_model* m, const int64_t* cell_idx,
                                const uint8_t* new_count, int32_t n, uint8_t* nverts,
-                               rjp_cell* cells, int32_t* status, void* stream) {
+                               rjp_cell* cells, int32_t* extents, void* stream) {
   if (!model_ok(m) || n < 0 || (n > 0 && (!cell_idx || !new_count)) || !nverts || !cells ||
-      !status)
+      !extents)
     return RJP_ERR_ARG;
-  return check_launch(rjp_launch_patch(m, cell_idx, new_count, n, nverts, cells, status,
+  return check_launch(rjp_launch_patch(m, cell_idx, new_count, n, nverts, cells, extents,
                                        (cudaStream_t)stream));
 }
 
@@ -96,10 +96,10 @@ extern "C" int rjp_cell_field(const rjp_model* m, const rjp_epoch* ep, const uin
 }
 
 extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_continuum* ct,
-                             const rjp_cell* cells, double* em, double* kff, double* tsum,
-                             int32_t* tcount, const rjp_line* ln, const rjp_channels* ch,
-                             int32_t nchan, int32_t contsub, double* tau_rrl,
-                             double* flux_rrl, void* stream) {
+                             const rjp_cell* cells, const int32_t* extents, double* em,
+                             double* kff, double* tsum, int32_t* tcount, const rjp_line* ln,
+                             const rjp_channels* ch, int32_t nchan, int32_t contsub,
+                             double* tau_rrl, double* flux_rrl, void* stream, void* stream2) {
   if (!model_ok(m) || !ep || !ct || !cells || !em || !kff || !tsum || !tcount || nchan < 0)
     return RJP_ERR_ARG;
   if (ep->n_blue < 0 || ep->n_blue > RJP_MAX_BURSTS || ep->n_red < 0 ||
@@ -109,10 +109,12 @@ extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_
     if (!ln || !ch || !ch->dnu || !ch->nu || !ch->cff || !ch->aff || !ch->bnu)
       return RJP_ERR_ARG;
     if (!tau_rrl && !flux_rrl) return RJP_ERR_ARG;
+    if (!extents) return RJP_ERR_ARG;
   }
-  return check_launch(rjp_launch_integrate(m, ep, ct, cells, em, kff, tsum, tcount, ln, ch,
-                                           nchan, contsub, tau_rrl, flux_rrl,
-                                           (cudaStream_t)stream));
+  return check_launch(rjp_launch_integrate(m, ep, ct, cells, extents, em, kff, tsum, tcount,
+                                           ln, ch, nchan, contsub, ln ? ln->dn_max : 0.0,
+                                           tau_rrl, flux_rrl, (cudaStream_t)stream,
+                                           (cudaStream_t)stream2));
 }
 
 extern "C" int rjp_continuum_images(const double* kff, const double* tsum,

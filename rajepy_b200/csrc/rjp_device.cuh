@@ -285,4 +285,49 @@ __device__ __forceinline__ double faddeeva_re(double x, double y) {
   return 2.0 * (pr * u2r - pi * u2i) + ur * 0.56418958354775628695;  // 1/sqrt(pi)
 }
 
+// 1/d for d in [L^2, 1e300): float seed + two Newton steps (no special cases to handle;
+// the result is within 1 ulp, which is all the rational approximation needs).
+__device__ __forceinline__ double rcp_pos(double d) {
+  double r = (double)__frcp_rn((float)d);
+  r = r * fma(-d, r, 2.0);          // 2^-24 -> 2^-48
+  r = fma(r, fma(-d, r, 1.0), r);   // -> rounding-limited
+  return r;
+}
+
+// The same for NV independent arguments sharing y: the NV recurrences are interleaved
+// so that the fp64 pipe always has independent FMAs in flight.
+template <int NV>
+__device__ __forceinline__ void faddeeva_re_n(const double* x, double y, double* out) {
+  const double L = RJP_WEIDEMAN_L;
+  const double dr = L + y, nr = L - y;
+  double inv[NV], s[NV], q[NV], zr[NV], zi[NV], b1[NV], b2[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    inv[v] = rcp_pos(fma(x[v], x[v], dr * dr));
+    zr[v] = (nr * dr - x[v] * x[v]) * inv[v];
+    zi[v] = (2.0 * L) * x[v] * inv[v];
+    s[v] = 2.0 * zr[v];
+    q[v] = zr[v] * zr[v] + zi[v] * zi[v];
+    b1[v] = 0.0;
+    b2[v] = 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < RJP_WEIDEMAN_N - 1; ++k) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const double b0 = fma(s[v], b1[v], fma(-q[v], b2[v], c_weideman[k]));
+      b2[v] = b1[v];
+      b1[v] = b0;
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const double pr = c_weideman[RJP_WEIDEMAN_N - 1] + zr[v] * b1[v] - q[v] * b2[v];
+    const double pi = zi[v] * b1[v];
+    const double ur = dr * inv[v], ui = x[v] * inv[v];
+    const double u2r = ur * ur - ui * ui, u2i = 2.0 * ur * ui;
+    out[v] = 2.0 * (pr * u2r - pi * u2i) + ur * 0.56418958354775628695;
+  }
+}
+
 }  // namespace rjp

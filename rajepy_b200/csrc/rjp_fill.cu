@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(FILL_THREADS)
 fill_grid_kernel(const rjp_model m, uint8_t* __restrict__ nverts,
                  rjp_cell* __restrict__ cells, int32_t* __restrict__ ties,
                  int32_t tie_capacity, int32_t* __restrict__ n_ties,
-                 int32_t* __restrict__ status) {
+                 int32_t* __restrict__ extents) {
   __shared__ uint8_t s_in[NVERT];
   const int tiles_z = (m.nz + TZ - 1) / TZ;
   const int tiles_y = (m.ny + TY - 1) / TY;
@@ -72,16 +72,27 @@ fill_grid_kernel(const rjp_model m, uint8_t* __restrict__ nverts,
     const size_t idx = ((size_t)(ix - m.x_lo) * m.ny + iy) * m.nz + iz;
     nverts[idx] = (uint8_t)cnt;
     rjp_cell c = {0.0, 0.0};
-    if (cnt > 0) c = pack_cell(m, ix, iy, iz, cnt);
+    if (cnt > 0) {
+      c = pack_cell(m, ix, iy, iz, cnt);
+      // y-extent of the ray's in-jet cells, for the channel loop (K4)
+      int32_t* e = extents + 2 * ((size_t)(ix - m.x_lo) * m.nz + iz);
+      atomicMin(e, iy);
+      atomicMax(e + 1, iy + 1);
+    }
     reinterpret_cast<double2*>(cells)[idx] = make_double2(c.ne0, c.temp);
   }
+}
+
+__global__ void init_extents_kernel(int2* __restrict__ extents, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) extents[i] = make_int2(2147483647, 0);
 }
 
 __global__ void patch_cells_kernel(const rjp_model m, const int64_t* __restrict__ cell_idx,
                                    const uint8_t* __restrict__ new_count, int32_t n,
                                    uint8_t* __restrict__ nverts,
                                    rjp_cell* __restrict__ cells,
-                                   int32_t* __restrict__ status) {
+                                   int32_t* __restrict__ extents) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t idx = cell_idx[i];
@@ -91,7 +102,12 @@ __global__ void patch_cells_kernel(const rjp_model m, const int64_t* __restrict_
   const int cnt = new_count[i];
   nverts[idx] = (uint8_t)cnt;
   rjp_cell c = {0.0, 0.0};
-  if (cnt > 0) c = pack_cell(m, ix, iy, iz, cnt);
+  if (cnt > 0) {
+    c = pack_cell(m, ix, iy, iz, cnt);
+    int32_t* e = extents + 2 * ((size_t)(ix - m.x_lo) * m.nz + iz);
+    atomicMin(e, iy);
+    atomicMax(e + 1, iy + 1);
+  }
   cells[idx] = c;
 }
 
@@ -152,22 +168,25 @@ using namespace rjp;
 
 extern "C" int rjp_launch_fill(const rjp_model* m, uint8_t* nverts, rjp_cell* cells,
                                int32_t* ties, int32_t tie_capacity, int32_t* n_ties,
-                               int32_t* status, cudaStream_t stream) {
+                               int32_t* extents, cudaStream_t stream) {
   const int nxs = m->x_hi - m->x_lo;
+  const size_t nray = (size_t)nxs * m->nz;
+  init_extents_kernel<<<(unsigned)((nray + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<int2*>(extents), nray);
   const long long tiles = (long long)((nxs + TX - 1) / TX) * ((m->ny + TY - 1) / TY) *
                           ((m->nz + TZ - 1) / TZ);
   if (tiles <= 0 || tiles > 2147483647LL) return RJP_ERR_ARG;
   fill_grid_kernel<<<(unsigned)tiles, FILL_THREADS, 0, stream>>>(
-      *m, nverts, cells, ties, tie_capacity, n_ties, status);
+      *m, nverts, cells, ties, tie_capacity, n_ties, extents);
   return RJP_OK;
 }
 
 extern "C" int rjp_launch_patch(const rjp_model* m, const int64_t* cell_idx,
                                 const uint8_t* new_count, int32_t n, uint8_t* nverts,
-                                rjp_cell* cells, int32_t* status, cudaStream_t stream) {
+                                rjp_cell* cells, int32_t* extents, cudaStream_t stream) {
   if (n <= 0) return RJP_OK;
   patch_cells_kernel<<<(n + 127) / 128, 128, 0, stream>>>(*m, cell_idx, new_count, n,
-                                                         nverts, cells, status);
+                                                         nverts, cells, extents);
   return RJP_OK;
 }
 

@@ -1,38 +1,42 @@
 // Line-of-sight integration for sm_100a: K3 (continuum sums), K4 (LTE recombination-
-// line opacity over all velocity channels) and K5 (image/cube epilogue) in ONE pass
-// over the packed 16-byte cell state, so each cell is read from HBM exactly once.
+// line opacity over all velocity channels) and K5 (image / cube epilogue).
 //
-// Mapping: a CTA owns ZT = 32 adjacent rays (fixed x, 32 consecutive z) over the whole
-// line of sight (y).  Lanes run along z, so every warp-wide load is one contiguous
-// 512-byte row of 16-byte cells; warps stride along y and keep RPW rows in flight each.
-// Sums are accumulated in fp64 registers per (warp, ray) and reduced across the CTA's
-// warps through shared memory at the end -- no atomics, deterministic order.
+// K3 `integrate_continuum_kernel` -- the dense sweep: every 16-byte cell of the slab is
+// read from HBM exactly once.  A CTA owns 32 adjacent rays (fixed x, 32 consecutive z)
+// over the whole line of sight; lanes run along z so every warp-wide load is one
+// contiguous 512-byte row, warps stride along y with RPW rows in flight each.  Sums
+// are fp64 registers per (warp, ray), reduced across the CTA's warps through shared
+// memory -- no atomics, deterministic order.  HBM-bound.
 //
-// The continuum part is HBM-bound (a handful of fp64 ops per in-jet cell, nothing for
-// the empty ones).  The line part is fp64-pipe-bound: in-jet cells of a chunk of rows
-// are compacted into a small shared-memory work list (channel-independent factors are
-// computed once per cell), then the CTA switches to thread <-> channel and every
-// thread accumulates its channel(s) over the list into a private row of the
-// shared-memory tau_L[channel][ray] accumulator; the next chunk's rows are already in
-// flight (register prefetch) while the Voigt profiles are evaluated.
+// K4 `integrate_line_kernel` -- the channel loop: fp64-pipe bound, so it is shaped for
+// the math, not for streaming.  The fill recorded, per ray, the y-extent [y_lo, y_hi)
+// of its in-jet cells; a CTA owns ZTr adjacent rays and NG groups of 8 channels,
+// thread (g, r) accumulates tau_L of channels 8g..8g+7 of ray r in REGISTERS while it
+// walks the ray's extent.  Channel-independent factors of a cell (burst factor, Doppler
+// shift, widths, amplitude) are computed once by one thread and shared through a small
+// shared-memory list.  Cells outside the extents are never touched, so K4 re-reads only
+// the in-jet cells (< 1 % of the grid); rays that miss the jet just write 0 / NaN.
+// K3 and K4 are independent and are launched on two streams so that the HBM-bound sweep
+// overlaps the compute-bound channel loop.
 #include "rjp_device.cuh"
 
 namespace rjp {
 
-constexpr int ZT = 32;          // rays per CTA
+constexpr int ZT = 32;          // rays per CTA of the dense sweep
 constexpr int RPW = 8;          // rows in flight per warp
-constexpr int LCAP = 256;       // work-list capacity (entries)
-constexpr int TAU_LD = ZT + 1;  // padded leading dimension of tau_s
+constexpr int GCH = 8;          // channels per thread of the line kernel
+constexpr int LINE_THREADS = 256;
 
 struct LineEntry {   // channel-independent factors of one in-jet cell (rrls.py:329-389)
   double xs;         // -(nu0_cell - nu0) / (sigma sqrt2)
   double inv_s2;     // 1 / (sigma sqrt2)
   double y;          // (dnu_L / 2) / (sigma sqrt2)
-  double amp;        // kappa0 n_e^2 T^-1.5 exp(Z^2 E_n / kT) ff / (sigma sqrt2)
+  double amp;        // kappa0 n_e^2 T^-1.5 exp(Z^2 E_n / kT) ff / (sigma sqrt2); 0 = skip
   double p0;         // 1 - exp(-h nu0 / kT)
-  double hk;         // h / (k T)
-  int ray;
-  int pad;
+  double hk;         // h / (k T); negative: |hk * dn| is small for every channel, use a1..a3
+  double a1, a2;     // 1 - exp(-h nu/kT) = p0 + dn (a1 + dn (a2 + dn a3)) + O((hk dn)^4)
+  double a3;
+  double pad;
 };
 
 __device__ __forceinline__ double2 ld_cell(const double2* p) {
@@ -227,14 +231,10 @@ integrate_continuum_kernel(const rjp_model m, const rjp_epoch ep, const rjp_cont
                    (size_t)xl * m.nz + iz, active, nullptr);
 }
 
-// ------------------------------------------------------------------ continuum + line
-__device__ __forceinline__ bool line_valid(const double2& c) {
-  return c.x > 0.0 && fabs(c.y) > 0.0;
-}
-
+// ------------------------------------------------------------------ line channels (K4)
 __device__ __noinline__ LineEntry make_entry(const Decoded& d, const rjp_model& m,
-                                             const rjp_line& ln, int ix, int iy, int iz,
-                                             int ray) {
+                                             const rjp_line& ln, double dn_max, int ix,
+                                             int iy, int iz) {
   LineEntry e;
   const double vlos = velocity_of(m, centroid_rw(m, ix, iy, iz)).vlos_rel + m.v_lsr;
   const double shift = -ln.nu0 * (vlos * ln.dopp);           // nu0_cell - nu0 (physics.py:558)
@@ -245,162 +245,136 @@ __device__ __noinline__ LineEntry make_entry(const Decoded& d, const rjp_model& 
   e.y = ln.stark * d.ne * e.inv_s2;                          // rrls.py:101, :353
   e.hk = ln.h_over_k / d.temp;
   e.p0 = -expm1(-e.hk * ln.nu0);
+  // Taylor coefficients of (1 - p0)(1 - exp(-hk dn)) in dn; used when |hk dn| <= 1e-3
+  // for all channels (error <= (1e-3)^4 / 24 relative), see planck_factor()
+  e.a1 = (1.0 - e.p0) * e.hk;
+  e.a2 = -0.5 * e.a1 * e.hk;
+  e.a3 = (1.0 / 6.0) * e.a1 * e.hk * e.hk;
+  e.pad = 0.0;
+  if (e.hk * dn_max <= 1e-3) e.hk = -e.hk;
   // rrls.py:383-389 with n_i = (X mu'/m_amu) n_e, times path length and 1/(sigma sqrt(2 pi))
   e.amp = ln.kappa0 * d.ne * d.ne * d.ffw / (d.temp * sqrt(d.temp)) *
           exp(ln.en_over_k / d.temp) * e.inv_s2;
-  if (!(vlos == vlos) || !d.ne_ok) {  // NaN velocity/density: nansum drops the cell
-    e.amp = 0.0; e.xs = 0.0; e.inv_s2 = 0.0; e.y = 1.0;
-  }
-  e.ray = ray;
-  e.pad = 0;
+  // NaN velocity / density / temperature: the reference's nansum drops the cell
+  if (!(vlos == vlos) || !d.ne_ok || !d.t_ok || !(e.amp == e.amp)) e.amp = 0.0;
   return e;
 }
 
-__device__ __forceinline__ double line_term(const LineEntry& e, double dn) {
-  const double x = fma(dn, e.inv_s2, e.xs);
-  const double wr = faddeeva_re(x, e.y);
-  const double d = e.hk * dn;
-  double om;  // 1 - exp(-d)
-  if (fabs(d) < 0.02)
-    om = d * (1.0 + d * (-0.5 + d * (1.0 / 6.0 + d * (-1.0 / 24.0 + d * (1.0 / 120.0)))));
-  else
-    om = -expm1(-d);
-  const double p4 = e.p0 + (1.0 - e.p0) * om;  // 1 - exp(-h nu / kT)  (rrls.py:387)
-  return e.amp * wr * p4;
+// 1 - exp(-h nu / kT) for nu = nu0 + dn from the cell's value at nu0 (rrls.py:387)
+__device__ __forceinline__ double planck_factor(const LineEntry& e, double dn) {
+  if (e.hk < 0.0) return fma(dn, fma(dn, fma(dn, e.a3, e.a2), e.a1), e.p0);
+  return e.p0 + (1.0 - e.p0) * (-expm1(-e.hk * dn));
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LINE_THREADS, 2)
 integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
                       const rjp_line ln, const rjp_channels ch, const int nchan,
-                      const int contsub, const double2* __restrict__ cells,
-                      double* __restrict__ em, double* __restrict__ kff,
-                      double* __restrict__ tsum, int32_t* __restrict__ tcount,
-                      double* __restrict__ tau_rrl, double* __restrict__ flux_rrl) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                      const int contsub, const int ng_log2, const double dn_max,
+                      const double2* __restrict__ cells,
+                      const int2* __restrict__ extents, double* __restrict__ tau_rrl,
+                      double* __restrict__ flux_rrl) {
   __shared__ Params s_p;
+  __shared__ rjp_line s_ln;
+  __shared__ LineEntry s_list[LINE_THREADS];
+  __shared__ double s_part[3][LINE_THREADS];
+  __shared__ int s_pcnt[LINE_THREADS];
   stage_params(&s_p, m, ep);
-  const int nwarps = blockDim.x >> 5;
-  double* tau_s = reinterpret_cast<double*>(smem_raw);                 // [nchan][TAU_LD]
-  LineEntry* list = reinterpret_cast<LineEntry*>(tau_s + (size_t)nchan * TAU_LD);
-  double* s_red = reinterpret_cast<double*>(list + LCAP);              // [3][nwarps][ZT]
-  double* s_out = s_red + 3 * nwarps * ZT;                             // [3][ZT]
-  int* s_cnt = reinterpret_cast<int*>(s_out + 3 * ZT);                 // [nwarps][ZT]
-  int* s_scan = s_cnt + nwarps * ZT;                                   // [nwarps + 1]
+  if (threadIdx.x == 0) s_ln = ln;
 
-  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-  const int ztiles = (m.nz + ZT - 1) / ZT;
+  const int NG = 1 << ng_log2;              // channel groups per ray
+  const int ZTr = blockDim.x >> ng_log2;    // rays per CTA
+  const int t = threadIdx.x;
+  const int r = t & (ZTr - 1), g = t / ZTr;
+  const int ztiles = (m.nz + ZTr - 1) / ZTr;
   const int xl = blockIdx.x / ztiles;
-  const int z0 = (blockIdx.x % ztiles) * ZT;
-  const int iz = z0 + lane;
+  const int iz = (blockIdx.x % ztiles) * ZTr + r;
   const bool active = iz < m.nz;
-  const double2* base = cells + (size_t)xl * m.ny * m.nz + (active ? iz : 0);
-  const int nxs = m.x_hi - m.x_lo;
   const int ix = m.x_lo + xl;
-  const Ray ray = ray_of(s_p.m, ix, iz);
+  const int nxs = m.x_hi - m.x_lo;
+  const size_t pix = (size_t)xl * m.nz + (active ? iz : 0);
+  const size_t plane = (size_t)nxs * m.nz;
 
-  for (int i = tid; i < nchan * TAU_LD; i += blockDim.x) tau_s[i] = 0.0;
-
-  ContAcc a = {0.0, 0.0, 0.0, 0};
-  const int chunk = nwarps * RPW;
-  double2 nxt[RPW];
+  int2 ext = make_int2(0, 0);
+  if (active) ext = extents[pix];
+  if (ext.x >= ext.y) ext = make_int2(0, 0);  // ray misses the jet
+  const int k0 = g * GCH;
+  double dn[GCH];
 #pragma unroll
-  for (int j = 0; j < RPW; ++j) {
-    const int y = wrp + j * nwarps;
-    nxt[j] = (active && y < m.ny) ? ld_cell(base + (size_t)y * m.nz) : make_double2(0.0, 0.0);
-  }
+  for (int j = 0; j < GCH; ++j) dn[j] = (k0 + j < nchan) ? __ldg(ch.dnu + k0 + j) : 0.0;
+  double acc[GCH];
+#pragma unroll
+  for (int j = 0; j < GCH; ++j) acc[j] = 0.0;
+  ContAcc ca = {0.0, 0.0, 0.0, 0};
+  const Ray ray = ray_of(s_p.m, ix, active ? iz : 0);
+  const double2* col = cells + (size_t)xl * m.ny * m.nz + (active ? iz : 0);
   __syncthreads();
 
-  for (int yc = 0; yc < m.ny; yc += chunk) {
-    double2 cur[RPW];
-#pragma unroll
-    for (int j = 0; j < RPW; ++j) cur[j] = nxt[j];
-    // prefetch the next chunk: in flight while this chunk's profiles are evaluated
-    if (yc + chunk < m.ny) {
-#pragma unroll
-      for (int j = 0; j < RPW; ++j) {
-        const int y = yc + chunk + wrp + j * nwarps;
-        nxt[j] = (active && y < m.ny) ? ld_cell(base + (size_t)y * m.nz)
-                                      : make_double2(0.0, 0.0);
+  for (int y0 = ext.x; __syncthreads_or(y0 < ext.y); y0 += NG) {
+    // phase 1: the ray's NG threads each prepare one cell of the extent
+    const int iy = y0 + g;
+    LineEntry e;
+    e.amp = 0.0;
+    if (iy < ext.y) {
+      const double2 c = col[(size_t)iy * m.nz];
+      if (!empty_cell(c)) {
+        const Decoded d = decode(c, s_p, ray, ix, iy, iz);
+        accumulate(ca, d, ct.t_exponent);
+        if (d.ne_ok && d.t_ok) e = make_entry(d, s_p.m, s_ln, dn_max, ix, iy, iz);
       }
     }
-    int mine = 0;
-#pragma unroll
-    for (int j = 0; j < RPW; ++j) {
-      if (empty_cell(cur[j])) continue;
-      accumulate(a, decode(cur[j], s_p, ray, ix, yc + wrp + j * nwarps, iz), ct.t_exponent);
-      mine += line_valid(cur[j]) ? 1 : 0;
-    }
-    if (!__syncthreads_or(mine > 0)) continue;  // chunk has no line-emitting cell
-
-    // block-wide exclusive scan of `mine`
-    int incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_scan[wrp] = incl;
+    s_list[r * NG + g] = e;
     __syncthreads();
-    int wbase = 0, total = 0;
-    for (int w = 0; w < nwarps; ++w) {
-      const int v = s_scan[w];
-      if (w < wrp) wbase += v;
-      total += v;
-    }
-    const int my_first = wbase + incl - mine;
-
-    for (int r0 = 0; r0 < total; r0 += LCAP) {
-      int rank = my_first;
+    // phase 2: thread (g, r) adds every cell of ray r to its 8 channels
+    const int n = min(NG, ext.y - y0);
+    for (int i = 0; i < n; ++i) {
+      const LineEntry en = s_list[r * NG + i];
+      if (en.amp == 0.0) continue;
 #pragma unroll
-      for (int j = 0; j < RPW; ++j) {
-        if (!line_valid(cur[j])) continue;
-        if (rank >= r0 && rank < r0 + LCAP)
-          list[rank - r0] = make_entry(decode(cur[j], s_p, ray, ix, yc + wrp + j * nwarps, iz),
-                                       s_p.m, ln, ix, yc + wrp + j * nwarps, iz, lane);
-        ++rank;
+      for (int h = 0; h < GCH; h += 4) {
+        double x[4], w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = fma(dn[h + j], en.inv_s2, en.xs);
+        faddeeva_re_n<4>(x, en.y, w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          acc[h + j] += en.amp * w[j] * planck_factor(en, dn[h + j]);
       }
-      __syncthreads();
-      const int nlist = min(LCAP, total - r0);
-      for (int c = tid; c < nchan; c += blockDim.x) {
-        const double dn = __ldg(ch.dnu + c);
-        double* row = tau_s + (size_t)c * TAU_LD;
-        int e = 0;
-        for (; e + 1 < nlist; e += 2) {
-          const LineEntry ea = list[e], eb = list[e + 1];
-          const double va = line_term(ea, dn), vb = line_term(eb, dn);
-          row[ea.ray] += va;
-          row[eb.ray] += vb;
-        }
-        if (e < nlist) {
-          const LineEntry ea = list[e];
-          row[ea.ray] += line_term(ea, dn);
-        }
-      }
-      __syncthreads();
     }
   }
 
-  reduce_and_store(a, ct, s_red, s_cnt, nwarps, em, kff, tsum, tcount,
-                   (size_t)xl * m.nz + iz, active, s_out);
-  __syncthreads();
+  // per-ray continuum sums (needed by the flux epilogue): reduce the NG partials of ray r
+  double kray = 0.0, ts = 0.0;
+  int cn = 0;
+  if (__syncthreads_or(ext.x < ext.y)) {  // some ray of this tile crosses the jet
+    s_part[0][r * NG + g] = ca.kff;
+    s_part[1][r * NG + g] = ca.tsum;
+    s_pcnt[r * NG + g] = ca.cnt;
+    __syncthreads();
+    if (ext.x < ext.y) {
+      for (int i = 0; i < NG; ++i) {
+        kray += s_part[0][r * NG + i];
+        ts += s_part[1][r * NG + i];
+        cn += s_pcnt[r * NG + i];
+      }
+    }
+    kray *= ct.tau_scale;
+  }
+  if (!active) return;
 
   // K5 epilogue: rrls.py:444-447, physics.py:571-574, classes.py:1323-1328, :1484-1488
-  const double kray = s_out[0 * ZT + lane];
-  const double cntr = s_out[2 * ZT + lane];
-  const double tmean = s_out[1 * ZT + lane] / cntr;  // NaN for rays that miss the jet
-  const size_t plane = (size_t)nxs * m.nz;
-  const size_t pix = (size_t)xl * m.nz + iz;
-  for (int c = wrp; c < nchan; c += nwarps) {
-    const double tl = tau_s[(size_t)c * TAU_LD + lane];
-    if (!active) continue;
-    if (tau_rrl) tau_rrl[(size_t)c * plane + pix] = tl;
+  const double tmean = ts / (double)cn;  // NaN for rays that miss the jet
+#pragma unroll
+  for (int j = 0; j < GCH; ++j) {
+    const int c = k0 + j;
+    if (c >= nchan) break;
+    if (tau_rrl) tau_rrl[(size_t)c * plane + pix] = acc[j];
     if (flux_rrl) {
       double s = dnan();
-      if (cntr > 0.0) {
+      if (cn > 0) {
         const double tc = __ldg(ch.cff + c) * kray;
         const double ec = exp(-tc);
         const double bnu = __ldg(ch.bnu + c) / (exp(ln.h_over_k * __ldg(ch.nu + c) / tmean) - 1.0);
-        s = bnu * ec * (1.0 - exp(-tl));
+        s = bnu * ec * (1.0 - exp(-acc[j]));
         if (!contsub) s += __ldg(ch.aff + c) * (tmean * (1.0 - ec));
       }
       flux_rrl[(size_t)c * plane + pix] = s;
@@ -438,36 +412,58 @@ __global__ void continuum_images_kernel(const double* __restrict__ kff,
 
 using namespace rjp;
 
-extern "C" size_t rjp_line_smem_bytes(int nchan, int nthreads) {
-  const int nwarps = nthreads / 32;
-  return (size_t)nchan * TAU_LD * 8 + (size_t)LCAP * sizeof(LineEntry) +
-         (size_t)3 * nwarps * ZT * 8 + 3 * ZT * 8 + (size_t)nwarps * ZT * 4 +
-         (size_t)(nwarps + 1) * 4 + 16;
-}
-
 extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
                                     const rjp_continuum* ct, const rjp_cell* cells,
-                                    double* em, double* kff, double* tsum, int32_t* tcount,
-                                    const rjp_line* ln, const rjp_channels* ch, int nchan,
-                                    int contsub, double* tau_rrl, double* flux_rrl,
-                                    cudaStream_t stream) {
+                                    const int32_t* extents, double* em, double* kff,
+                                    double* tsum, int32_t* tcount, const rjp_line* ln,
+                                    const rjp_channels* ch, int nchan, int contsub,
+                                    double dn_max, double* tau_rrl, double* flux_rrl,
+                                    cudaStream_t stream, cudaStream_t stream2) {
   const int nxs = m->x_hi - m->x_lo;
   const long long ctas = (long long)nxs * ((m->nz + ZT - 1) / ZT);
   if (ctas <= 0 || ctas > 2147483647LL) return RJP_ERR_ARG;
   const double2* c4 = reinterpret_cast<const double2*>(cells);
-  if (nchan <= 0 || ln == nullptr) {
-    integrate_continuum_kernel<<<(unsigned)ctas, 256, 0, stream>>>(*m, *ep, *ct, c4, em, kff,
-                                                                  tsum, tcount);
-    return RJP_OK;
+  const bool lines = nchan > 0 && ln != nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaStream_t ls = stream;
+  if (lines && stream2 != nullptr && stream2 != stream) {
+    // fork: the channel loop runs beside the dense sweep
+    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess)
+      return RJP_ERR_CUDA;
+    cudaEventRecord(fork, stream);
+    cudaStreamWaitEvent(stream2, fork, 0);
+    ls = stream2;
   }
-  const int threads = 256;
-  const size_t smem = rjp_line_smem_bytes(nchan, threads);
-  if (smem > 227 * 1024) return RJP_ERR_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(integrate_line_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return RJP_ERR_CUDA;
-  integrate_line_kernel<<<(unsigned)ctas, threads, smem, stream>>>(
-      *m, *ep, *ct, *ln, *ch, nchan, contsub, c4, em, kff, tsum, tcount, tau_rrl, flux_rrl);
+  integrate_continuum_kernel<<<(unsigned)ctas, 256, 0, stream>>>(*m, *ep, *ct, c4, em, kff,
+                                                                tsum, tcount);
+  if (lines) {
+    // channel blocks of at most 8 * 256 channels per launch
+    for (int c0 = 0; c0 < nchan; c0 += GCH * LINE_THREADS) {
+      const int nc = (nchan - c0 < GCH * LINE_THREADS) ? nchan - c0 : GCH * LINE_THREADS;
+      const int groups = (nc + GCH - 1) / GCH;
+      int ng_log2 = 0;
+      while ((1 << ng_log2) < groups) ++ng_log2;
+      int ztr = LINE_THREADS >> ng_log2;
+      if (ztr > 32) ztr = 32;
+      const int threads = ztr << ng_log2;
+      const long long tiles = (long long)nxs * ((m->nz + ztr - 1) / ztr);
+      if (tiles > 2147483647LL) return RJP_ERR_ARG;
+      rjp_channels cb = *ch;
+      cb.dnu += c0; cb.nu += c0; cb.cff += c0; cb.aff += c0; cb.bnu += c0;
+      const size_t off = (size_t)c0 * nxs * m->nz;
+      integrate_line_kernel<<<(unsigned)tiles, threads, 0, ls>>>(
+          *m, *ep, *ct, *ln, cb, nc, contsub, ng_log2, dn_max, c4,
+          reinterpret_cast<const int2*>(extents), tau_rrl ? tau_rrl + off : nullptr,
+          flux_rrl ? flux_rrl + off : nullptr);
+    }
+  }
+  if (fork) {
+    cudaEventRecord(join, stream2);
+    cudaStreamWaitEvent(stream, join, 0);
+    cudaEventDestroy(fork);
+    cudaEventDestroy(join);
+  }
   return RJP_OK;
 }
 

@@ -194,6 +194,10 @@ def gff(freq, temp, z=1.):
     from scipy.interpolate import bisplev, bisplrep
     scalar = np.isscalar(freq)
     freqs = np.atleast_1d(np.asarray(freq, dtype=np.float64))
+    key = (freqs.tobytes(), float(temp), float(z))
+    hit = _GFF_CACHE.get(key)
+    if hit is not None:
+        return float(hit[0]) if scalar else hit.copy()
     ry = con.m_e * con.e ** 4. / (8 * con.epsilon_0 ** 2. * con.h ** 2.)
     logg2 = float(np.log10(z ** 2. * ry / (con.k * temp)))
     logus = np.log10(con.h * freqs / (con.k * temp))
@@ -210,7 +214,13 @@ def gff(freq, temp, z=1.):
         for i in np.flatnonzero(rows == row):
             out[i] = np.ravel(bisplev(np.atleast_1d(logg2), np.atleast_1d(logus[i]),
                                       tck))[0]
+    if len(_GFF_CACHE) > 256:
+        _GFF_CACHE.clear()
+    _GFF_CACHE[key] = out.copy()
     return float(out[0]) if scalar else out
+
+
+_GFF_CACHE = {}
 
 
 # ----------------------------------------------------------------- recombination lines

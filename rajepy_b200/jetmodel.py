@@ -174,6 +174,7 @@ class JetModel:
         self._cont = None      # cached continuum pass (device tensors)
         self._line = None      # cached line pass
         self._timings = {}
+        self._coeff_cache = {}
 
     # ------------------------------------------------------------------ text table
     def __str__(self):
@@ -496,14 +497,16 @@ class JetModel:
             nverts = torch.empty(ncell, dtype=torch.uint8, device=dev)
             cells = torch.empty((ncell, 2), dtype=torch.float64, device=dev)
             ties = torch.empty((_TIE_CAPACITY, 4), dtype=torch.int32, device=dev)
-            counters = torch.zeros(8, dtype=torch.int32, device=dev)  # [0] n_ties, [4:8] status
+            counters = torch.zeros(8, dtype=torch.int32, device=dev)  # [0] n_ties
+            nray = (self._x_hi - self._x_lo) * self._nz
+            extents = torch.empty((nray, 2), dtype=torch.int32, device=dev)
             tie_cap = _TIE_CAPACITY
             m = self._model_struct()
             for attempt in range(3):
                 counters.zero_()
                 st = lib.rjp_fill_grid(m, nverts.data_ptr(), cells.data_ptr(),
                                        ties.data_ptr(), tie_cap, counters.data_ptr(),
-                                       counters.data_ptr() + 16, self._stream())
+                                       extents.data_ptr(), self._stream())
                 _cabi.check(st, "rjp_fill_grid")
                 _launched()
                 c = counters.cpu().numpy()
@@ -514,7 +517,8 @@ class JetModel:
             else:
                 raise _cabi.EngineError("grid fill: tie list did not converge")
             n_ties = int(c[0])
-            self._dev = {"nverts": nverts, "cells": cells, "model": m, "device": dev,
+            self._dev = {"nverts": nverts, "cells": cells, "extents": extents, "model": m,
+                         "device": dev, "stream2": torch.cuda.Stream(device=dev),
                          "n_ties": n_ties, "n_patched": 0}
             if n_ties > 0:
                 self._resolve_ties(ties[:n_ties].cpu().numpy().astype(np.int64))
@@ -569,10 +573,9 @@ class JetModel:
         if int(new.min()) < 0 or int(new.max()) > 8:
             raise _cabi.EngineError("tie resolution produced an impossible vertex count")
         new8 = new.to(torch.uint8)
-        status = torch.zeros(4, dtype=torch.int32, device=dev)
         st = lib.rjp_patch_cells(d["model"], idx.data_ptr(), new8.data_ptr(), idx.numel(),
                                  d["nverts"].data_ptr(), d["cells"].data_ptr(),
-                                 status.data_ptr(), self._stream())
+                                 d["extents"].data_ptr(), self._stream())
         _cabi.check(st, "rjp_patch_cells")
         _launched()
 
@@ -598,10 +601,10 @@ class JetModel:
             dev = d["device"]
             idx = torch.from_numpy(diff.astype(np.int64)).to(dev)
             new8 = torch.from_numpy(want[diff]).to(dev)
-            status = torch.zeros(4, dtype=torch.int32, device=dev)
             st = lib.rjp_patch_cells(d["model"], idx.data_ptr(), new8.data_ptr(),
                                      idx.numel(), d["nverts"].data_ptr(),
-                                     d["cells"].data_ptr(), status.data_ptr(), self._stream())
+                                     d["cells"].data_ptr(), d["extents"].data_ptr(),
+                                     self._stream())
             _cabi.check(st, "rjp_patch_cells")
         _launched()
         self._fields.clear()
@@ -719,6 +722,10 @@ class JetModel:
         self._overrides['vel'] = new_vs
         self._invalidate()
 
+    def release(self):
+        """Drop every device buffer held by the model (they are re-created on demand)."""
+        self._invalidate()
+
     def _invalidate(self):
         self._dev = None
         self._cont = None
@@ -735,12 +742,23 @@ class JetModel:
 
     def _ff_coeff(self, freqs):
         """tau_ff(nu) = coeff(nu) * K with K the frequency-independent ray sum
-        (classes.py:1388-1399, :1421-1429)."""
+        (classes.py:1388-1399, :1421-1429).  Cached: the Gaunt-factor spline fits are
+        host work that would otherwise sit between kernel launches."""
         freqs = np.asarray(freqs, dtype=np.float64)
+        key = (freqs.tobytes(), float(self._params['properties']['T_0']),
+               float(self._params['power_laws']['q_T']))
+        hit = self._coeff_cache.get(key)
+        if hit is not None:
+            return hit
         if self._params['power_laws']['q_T'] == 0.:
             g = hm.gff(freqs, self._params['properties']['T_0'])
-            return freqs ** -2. * g
-        return 11.95 * freqs ** -0.1 * freqs ** -2.
+            out = freqs ** -2. * g
+        else:
+            out = 11.95 * freqs ** -0.1 * freqs ** -2.
+        if len(self._coeff_cache) > 64:
+            self._coeff_cache.clear()
+        self._coeff_cache[key] = out
+        return out
 
     def _pixel_solid_angle(self):
         return float(np.arctan((self._csize * con.au) /
@@ -775,9 +793,9 @@ class JetModel:
             tau = flux = None
             if line is None:
                 st = lib.rjp_integrate(d["model"], ep, ct, d["cells"].data_ptr(),
-                                       em.data_ptr(), kff.data_ptr(), tsum.data_ptr(),
-                                       cnt.data_ptr(), None, None, 0, 1, None, None,
-                                       self._stream())
+                                       d["extents"].data_ptr(), em.data_ptr(),
+                                       kff.data_ptr(), tsum.data_ptr(), cnt.data_ptr(), None,
+                                       None, 0, 1, None, None, self._stream(), None)
             else:
                 ln, chans, keep = self._line_structs(line, freqs, dev)
                 nch = len(freqs)
@@ -786,14 +804,15 @@ class JetModel:
                 if want_flux:
                     flux = torch.empty((nch, nxs, nz), dtype=torch.float64, device=dev)
                 st = lib.rjp_integrate(d["model"], ep, ct, d["cells"].data_ptr(),
-                                       em.data_ptr(), kff.data_ptr(), tsum.data_ptr(),
-                                       cnt.data_ptr(), ln, chans, nch, 1 if contsub else 0,
+                                       d["extents"].data_ptr(), em.data_ptr(),
+                                       kff.data_ptr(), tsum.data_ptr(), cnt.data_ptr(), ln,
+                                       chans, nch, 1 if contsub else 0,
                                        tau.data_ptr() if want_tau else None,
                                        flux.data_ptr() if want_flux else None,
-                                       self._stream())
+                                       self._stream(), d["stream2"].cuda_stream)
                 del keep
             _cabi.check(st, "rjp_integrate")
-            _launched()
+            _launched(1 if line is None else 1 + (len(freqs) + 2047) // 2048)
         self._cont = {"key": key_c, "em": em, "kff": kff, "tsum": tsum, "cnt": cnt}
         if line is None:
             return self._cont
@@ -818,6 +837,7 @@ class JetModel:
                           np.sqrt(np.pi))
         ln.en_over_k = float(z ** 2. * hm.energy_n(n, element) / hm.k_cgs)
         ln.h_over_k = float(hm.h_cgs / hm.k_cgs)
+        ln.dn_max = float(np.max(np.abs(freqs - nu0))) if freqs.size else 0.0
         omega_jy = self._pixel_solid_angle() / 1e-26
         host = np.stack([
             freqs - nu0,

@@ -28,10 +28,13 @@ def timed(fn, n=3):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    argv = sys.argv[1:]
     nchan = 256
-    if "--nchan" in sys.argv:
-        nchan = int(sys.argv[sys.argv.index("--nchan") + 1])
+    if "--nchan" in argv:
+        i = argv.index("--nchan")
+        nchan = int(argv[i + 1])
+        del argv[i:i + 2]
+    args = [a for a in argv if not a.startswith("--")]
     sizes = [int(a) for a in args] or [256]
     log = rb.logger.Log(os.path.join(tempfile.mkdtemp(), "q.log"), verbose=False)
     for n in sizes:
@@ -49,8 +52,8 @@ def main():
             cnt = torch.zeros(8, dtype=torch.int32, device="cuda")
             ties = torch.empty((1 << 16, 4), dtype=torch.int32, device="cuda")
             lib.rjp_fill_grid(d["model"], d["nverts"].data_ptr(), d["cells"].data_ptr(),
-                              ties.data_ptr(), 1 << 16, cnt.data_ptr(), cnt.data_ptr() + 16,
-                              jm._stream())
+                              ties.data_ptr(), 1 << 16, cnt.data_ptr(),
+                              d["extents"].data_ptr(), jm._stream())
         t_fill = timed(refill)
 
         def cont():
@@ -72,6 +75,7 @@ def main():
               f"  line x{nchan} {t_line:8.3f} ms  ({gb / t_line * 1e3:7.1f} GB/s, "
               f"{ncell * nchan / t_line / 1e6:.1f} Gcell.ch/s, "
               f"{injet * nchan / t_line / 1e6:.2f} G in-jet evals/s)", flush=True)
+        jm.release()
         del jm, d
         torch.cuda.empty_cache()
 
