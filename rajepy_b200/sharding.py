@@ -35,18 +35,20 @@ def gather_x(tile, nx, rank, world, dim=0, group=None):
         return tile
     if not dist.is_initialized():
         raise RuntimeError("sharded JetModel needs torch.distributed to be initialised")
-    sizes = [slab_bounds(nx, r, world) for r in range(world)]
+    sizes = [hi - lo for lo, hi in (slab_bounds(nx, r, world) for r in range(world))]
     tile = tile.contiguous()
-    shapes = []
-    for lo, hi in sizes:
-        shp = list(tile.shape)
-        shp[dim] = hi - lo
-        shapes.append(shp)
-    if len({tuple(s) for s in shapes}) == 1 and dim == 0:
-        out = torch.empty([world * tile.shape[0]] + list(tile.shape[1:]), dtype=tile.dtype,
+    if dim != 0:
+        tile = tile.movedim(dim, 0).contiguous()
+    big = max(sizes)
+    if tile.shape[0] < big:  # uneven split: pad to the largest slab (collectives need equal sizes)
+        pad = torch.zeros([big - tile.shape[0]] + list(tile.shape[1:]), dtype=tile.dtype,
                           device=tile.device)
-        dist.all_gather_into_tensor(out, tile, group=group)
-        return out
-    parts = [torch.empty(s, dtype=tile.dtype, device=tile.device) for s in shapes]
-    dist.all_gather(parts, tile, group=group)
-    return torch.cat(parts, dim=dim)
+        tile = torch.cat([tile, pad], dim=0)
+    out = torch.empty([world * big] + list(tile.shape[1:]), dtype=tile.dtype,
+                      device=tile.device)
+    dist.all_gather_into_tensor(out, tile, group=group)
+    if min(sizes) != big:
+        out = torch.cat([out[r * big: r * big + sizes[r]] for r in range(world)], dim=0)
+    if dim != 0:
+        out = out.movedim(0, dim).contiguous()
+    return out

@@ -1,0 +1,187 @@
+"""CPU tests of the host side: derived scalars, the C-ABI library and its header, FITS
+products, parameter files, sharding helpers.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+import tempfile
+
+import numpy as np
+import pytest
+import scipy.constants as con
+
+import rajepy_b200 as rb
+from rajepy_b200 import _cabi, fitsio, hostmath as hm, sharding
+from oracle import rajepy_oracle as orc
+from tests import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _model(params, **kw):
+    log = rb.logger.Log(os.path.join(tempfile.mkdtemp(), "m.log"), verbose=False)
+    return rb.JetModel(params, log=log, **kw)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _cabi.load()
+    hdr = open(os.path.join(ROOT, "include", "rajepy_b200.h")).read()
+    declared = set(re.findall(r"\b(rjp_[a-z_]+)\s*\(", hdr))
+    assert {"rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field", "rjp_integrate",
+            "rjp_continuum_images", "rjp_strerror"} <= declared
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in the header but not exported"
+    assert lib.rjp_abi_version() == 1
+    assert lib.rjp_strerror(0) == b"ok"
+    assert lib.rjp_strerror(-1) == b"invalid argument"
+
+
+def test_abi_rejects_bad_arguments_without_gpu():
+    lib = _cabi.load()
+    m = _cabi.Model()  # all zero: invalid dims
+    assert lib.rjp_fill_grid(m, None, None, None, 0, None, None, None) == _cabi.ERR_ARG
+    assert lib.rjp_continuum_images(None, None, None, 0, None, None, 1.0, 0, None, None,
+                                    None, None) == _cabi.ERR_ARG
+
+
+def test_struct_mirrors_match_header_sizes():
+    lib = _cabi.load()
+    sizes = [ctypes.c_int32() for _ in range(6)]
+    lib.rjp_struct_sizes(*[ctypes.byref(s) for s in sizes])
+    mirrors = (_cabi.Model, _cabi.Epoch, _cabi.Continuum, _cabi.Line, _cabi.Channels)
+    assert [s.value for s in sizes[:5]] == [ctypes.sizeof(t) for t in mirrors]
+    assert sizes[5].value == 16  # the 16-byte cell state
+
+
+@pytest.mark.parametrize("name", ["small", "inclined", "powerlaws", "nobursts"])
+def test_derived_parameters_match_oracle(name):
+    factory = cases.CASES[name][0]
+    jm, oj = _model(factory()), orc.OracleJet(factory())
+    assert (jm.nx, jm.ny, jm.nz) == (oj.nx, oj.ny, oj.nz)
+    for sec, key in (("geometry", "mod_r_0"), ("power_laws", "q_n"),
+                     ("power_laws", "q_tau"), ("properties", "n_0")):
+        assert jm.params[sec][key] == oj.p[sec][key]
+    assert jm.ss_jml('B') == oj.ss_bj and jm.ss_jml('R') == oj.ss_rj
+    t = np.linspace(-1, 3, 9) * con.year
+    np.testing.assert_allclose(jm.jml_t('B')(t), oj._jml('B', t), rtol=1e-14)
+    np.testing.assert_allclose(jm.jml_t('RB')(t), oj._jml('B', t) + oj._jml('R', t),
+                               rtol=1e-14)
+    ep = jm._epoch_struct()
+    assert ep.n_blue == len(oj.bursts['B']) and ep.n_red == len(oj.bursts['R'])
+
+
+def test_lz_grid_dims_and_param_file(tmp_path):
+    p = cases.base_params()
+    p["grid"]["l_z"] = 2.
+    assert (_model(p).nx, _model(p).ny, _model(p).nz) == (108, 110, 588)
+    f = tmp_path / "my-model-params.py"
+    f.write_text("import numpy as np\nparams = " + repr(cases.case_small())
+                 .replace("array", "np.array") + "\n")
+    jm = _model(str(f))
+    assert (jm.nx, jm.ny, jm.nz) == (20, 40, 60)
+    with pytest.raises(TypeError):
+        rb.JetModel(42)
+    with pytest.raises(FileNotFoundError):
+        rb.JetModel(str(tmp_path / "missing.py"))
+    bad = cases.case_small()
+    del bad["geometry"]["inc"]
+    assert isinstance(rb.check_model_params(bad), KeyError)
+
+
+def test_hostmath_matches_oracle_scalars():
+    assert hm.rrl_nu_0('H', 58, 1) == orc.rrl_nu_0('H', 58, 1)
+    assert hm.rrl_nu_0('He', 42, 2) == orc.rrl_nu_0('He', 42, 2)
+    assert hm.gff(5e9, 1e4) == pytest.approx(orc.gff(5e9, 1e4), rel=1e-14)
+    fr = np.logspace(9, 11.5, 7)
+    np.testing.assert_allclose(hm.gff(fr, 1e4), [orc.gff(f, 1e4) for f in fr], rtol=1e-13)
+    assert hm.ni_from_ne(1.0, 'H') == orc.ni_from_ne(1.0, 'H')
+    assert hm.f_n1n2(58, 1) == orc.f_n1n2(58, 1)
+    assert hm.rrl_parser('He42b') == ('He', 42, 2)
+    np.testing.assert_array_equal(hm.chan_freqs(1e10, 8e6, 1e6), orc.chan_freqs(1e10, 8e6, 1e6))
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    jm = _model(cases.case_small())
+    with pytest.raises(rb.EngineError):
+        jm.emission_measure()
+    with pytest.raises(rb.EngineError):
+        _ = jm.fill_factor
+    with pytest.raises(ValueError):
+        jm.intensity_rrl('H58a', 3e10, lte=False)
+
+
+def test_product_path_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "rajepy_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+
+
+def test_reorder_axes_semantics():
+    a = np.arange(2 * 3).reshape(2, 3).astype(float)          # (nx, nz)
+    assert np.array_equal(rb.reorder_axes(a, ra_axis=0, dec_axis=1), a.T)
+    c = np.arange(4 * 2 * 3).reshape(4, 2, 3).astype(float)   # (nf, nx, nz)
+    out = rb.reorder_axes(c, ra_axis=1, dec_axis=2, axis3=0, axis3_type='freq')
+    assert out.shape == (4, 3, 2)
+    assert np.array_equal(out, np.swapaxes(c, 1, 2))
+
+
+def test_fits_round_trip(tmp_path):
+    jm = _model(cases.case_small())
+    img = np.random.default_rng(0).normal(size=(jm.nx, jm.nz))
+    img[0, 0] = np.nan
+    f = str(tmp_path / "em.fits")
+    jm.save_fits(rb.reorder_axes(img, 0, 1), f, 'em')
+    hdr, data = fitsio.read_fits(f)
+    assert os.path.getsize(f) % 2880 == 0
+    assert data.shape == (jm.nz, jm.nx)
+    assert np.array_equal(np.nan_to_num(data), np.nan_to_num(img.T))
+    assert hdr['BITPIX'] == -64 and hdr['NAXIS1'] == jm.nx and hdr['NAXIS2'] == jm.nz
+    assert hdr['CTYPE1'] == 'RA---TAN' and hdr['CTYPE2'] == 'DEC--TAN'
+    assert hdr['CRPIX1'] == jm.nx / 2 + 0.5 and hdr['CRPIX2'] == jm.nz / 2 + 0.5
+    assert hdr['BUNIT'] == 'pc cm^-6' and hdr['OBJECT'] == 'test2'
+    ra, dec = fitsio.parse_sexagesimal("04:31:34.07736", "+18:08:04.9020")
+    assert hdr['CRVAL1'] == pytest.approx(15 * (4 + 31 / 60 + 34.07736 / 3600), abs=1e-12)
+    assert hdr['CRVAL2'] == pytest.approx(dec, abs=1e-12)
+    cdelt = np.degrees(np.arctan(0.5 * con.au / (120. * con.parsec)))
+    assert hdr['CDELT1'] == pytest.approx(-cdelt, rel=1e-14)
+    assert ''.join(hdr['HISTORY']).count('JET MODEL') == 1
+    # cube with a frequency axis (classes.py:1615-1629)
+    fr = np.array([1e9, 2e9, 3e9, 4e9])
+    cube = np.zeros((4, jm.nx, jm.nz))
+    f2 = str(tmp_path / "flux.fits")
+    jm.save_fits(rb.reorder_axes(cube, 1, 2, axis3=0, axis3_type='freq'), f2, 'flux', fr)
+    hdr, data = fitsio.read_fits(f2)
+    assert data.shape == (4, jm.nz, jm.nx)
+    assert hdr['CTYPE3'] == 'FREQ' and hdr['CDELT3'] == 1e9 and hdr['CRPIX3'] == 2.5
+    assert hdr['CRVAL3'] == 2e9 + 0.5e9 and hdr['BUNIT'] == 'Jy pixel^-1'
+    with pytest.raises(ValueError):
+        jm.save_fits(cube, f2, 'nonsense')
+
+
+def test_model_table_matches_reference_layout():
+    s = str(_model(cases.case_small()))
+    lines = s.split('\n')
+    assert lines[1].strip('/').strip() == 'JET MODEL'
+    assert len({len(ln) for ln in lines if ln}) == 1        # rectangular table
+    assert '|  epsilon  |' in s and '+0.778' in s and 'BURSTS' in s and '0.50' in s
+    assert 'None' in str(_model(cases.case_nobursts()))
+
+
+def test_slab_bounds_cover_grid():
+    for nx in (50, 64, 1024, 7):
+        for world in (1, 2, 3, 4, 7):
+            if world > nx:
+                continue
+            b = [sharding.slab_bounds(nx, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == nx
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+    assert sharding.epoch_shares(64, 3, 8) == list(range(3, 64, 8))
+    with pytest.raises(ValueError):
+        sharding.slab_bounds(4, 0, 8)
