@@ -300,10 +300,10 @@ def run_gpu(args):
                                  "the in-jet cells, see DESIGN.md"},
         }
         if world == 1 and not args.no_cpu_baseline:
-            dt, u = oracle_step(64, 16, 8)
+            dt, u = oracle_step(128, 16, 8)
             line_out["cpu_baseline"] = {
                 "value": u / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": "64^3 cells of the same jet, 16 continuum freqs + 8 H58a "
+                "sample": "128^3 cells of the same jet, 16 continuum freqs + 8 H58a "
                           "channels, numpy oracle (single-threaded like the reference), "
                           f"{dt:.1f} s"}
         print(json.dumps(line_out))

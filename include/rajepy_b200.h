@@ -172,9 +172,17 @@ enum {
 int rjp_cell_field(const rjp_model* m_host, const rjp_epoch* ep_host,
                    const uint8_t* nverts, int32_t field, double* out, void* stream);
 
+/* List of the rays whose extent is non-empty (slab-local ray index x_local * nz + z), in
+ * arbitrary order: the channel loop launches one CTA per listed ray.  `list` holds up to
+ * nray entries, *n_active (device) receives the count.  Call after rjp_fill_grid /
+ * rjp_patch_cells. */
+int rjp_ray_list(const int32_t* extents, int64_t nray, int32_t* list, int32_t* n_active,
+                 void* stream);
+
 /* Line-of-sight pass (K3+K4+K5).  The dense sweep reads every cell of the slab once
  * (continuum sums); the channel loop walks only the per-ray in-jet extents recorded by the
- * fill and runs beside the sweep on `stream2` when one is given (NULL: same stream).
+ * fill (one CTA per ray of `ray_list`, n_active of them) and runs beside the sweep on
+ * `stream2` when one is given (NULL: same stream).
  * Replaces emission_measure (classes.py:1101-1128), optical_depth_ff (:1353-1447),
  * the nanmean temperature of intensity_ff (:1471-1473), optical_depth_rrl (:1130-1229)
  * and intensity_rrl/flux_rrl (:1231-1351).
@@ -185,7 +193,8 @@ int rjp_cell_field(const rjp_model* m_host, const rjp_epoch* ep_host,
  * On return all work is ordered on `stream` (stream2 is joined back).              */
 int rjp_integrate(const rjp_model* m_host, const rjp_epoch* ep_host,
                   const rjp_continuum* cont_host, const rjp_cell* cells,
-                  const int32_t* extents, double* em, double* kff, double* tsum,
+                  const int32_t* extents, const int32_t* ray_list, int32_t n_active,
+                  double* em, double* kff, double* tsum,
                   int32_t* tcount, const rjp_line* line_host, const rjp_channels* ch_host,
                   int32_t nchan, int32_t contsub, double* tau_rrl, double* flux_rrl,
                   void* stream, void* stream2);

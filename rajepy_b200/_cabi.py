@@ -61,7 +61,7 @@ class EngineError(RuntimeError):
 _lib = None
 
 EXPORTS = ("rjp_strerror", "rjp_last_cuda_error", "rjp_abi_version", "rjp_struct_sizes",
-           "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field", "rjp_integrate",
+           "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field", "rjp_ray_list", "rjp_integrate",
            "rjp_continuum_images")
 
 
@@ -98,11 +98,13 @@ def load():
     lib.rjp_fill_grid.argtypes = [C.POINTER(Model), vp, vp, vp, i32, vp, vp, vp]
     lib.rjp_patch_cells.argtypes = [C.POINTER(Model), vp, vp, i32, vp, vp, vp, vp]
     lib.rjp_cell_field.argtypes = [C.POINTER(Model), C.POINTER(Epoch), vp, i32, vp, vp]
+    lib.rjp_ray_list.argtypes = [vp, i64, vp, vp, vp]
     lib.rjp_integrate.argtypes = [C.POINTER(Model), C.POINTER(Epoch), C.POINTER(Continuum),
-                                  vp, vp, vp, vp, vp, vp, C.POINTER(Line),
+                                  vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(Line),
                                   C.POINTER(Channels), i32, i32, vp, vp, vp, vp]
     lib.rjp_continuum_images.argtypes = [vp, vp, vp, i64, vp, vp, dbl, i32, vp, vp, vp, vp]
     for f in ("rjp_struct_sizes", "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field",
+              "rjp_ray_list",
               "rjp_integrate", "rjp_continuum_images"):
         getattr(lib, f).restype = C.c_int
     sizes = [i32() for _ in range(6)]

@@ -13,9 +13,10 @@ int rjp_launch_patch(const rjp_model*, const int64_t*, const uint8_t*, int32_t, 
 int rjp_launch_field(const rjp_model*, const rjp_epoch*, const uint8_t*, int32_t, double*,
                      cudaStream_t);
 int rjp_launch_integrate(const rjp_model*, const rjp_epoch*, const rjp_continuum*,
-                         const rjp_cell*, const int32_t*, double*, double*, double*, int32_t*,
-                         const rjp_line*, const rjp_channels*, int, int, double, double*,
-                         double*, cudaStream_t, cudaStream_t);
+                         const rjp_cell*, const int32_t*, const int32_t*, int, double*, double*,
+                         double*, int32_t*, const rjp_line*, const rjp_channels*, int, int,
+                         double, double*, double*, cudaStream_t, cudaStream_t);
+int rjp_launch_ray_list(const int32_t*, int, int32_t*, int32_t*, cudaStream_t);
 int rjp_launch_continuum_images(const double*, const double*, const int32_t*, int64_t,
                                 const double*, const double*, double, int, double*, double*,
                                 double*, cudaStream_t);
@@ -95,8 +96,16 @@ extern "C" int rjp_cell_field(const rjp_model* m, const rjp_epoch* ep, const uin
   return check_launch(rjp_launch_field(m, ep, nverts, field, out, (cudaStream_t)stream));
 }
 
+extern "C" int rjp_ray_list(const int32_t* extents, int64_t nray, int32_t* list,
+                            int32_t* n_active, void* stream) {
+  if (!extents || !list || !n_active || nray < 0 || nray > 2147483647LL) return RJP_ERR_ARG;
+  return check_launch(rjp_launch_ray_list(extents, (int)nray, list, n_active,
+                                          (cudaStream_t)stream));
+}
+
 extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_continuum* ct,
-                             const rjp_cell* cells, const int32_t* extents, double* em,
+                             const rjp_cell* cells, const int32_t* extents,
+                             const int32_t* ray_list, int32_t n_active, double* em,
                              double* kff, double* tsum, int32_t* tcount, const rjp_line* ln,
                              const rjp_channels* ch, int32_t nchan, int32_t contsub,
                              double* tau_rrl, double* flux_rrl, void* stream, void* stream2) {
@@ -109,9 +118,10 @@ extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_
     if (!ln || !ch || !ch->dnu || !ch->nu || !ch->cff || !ch->aff || !ch->bnu)
       return RJP_ERR_ARG;
     if (!tau_rrl && !flux_rrl) return RJP_ERR_ARG;
-    if (!extents) return RJP_ERR_ARG;
+    if (!extents || n_active < 0 || (n_active > 0 && !ray_list)) return RJP_ERR_ARG;
   }
-  return check_launch(rjp_launch_integrate(m, ep, ct, cells, extents, em, kff, tsum, tcount,
+  return check_launch(rjp_launch_integrate(m, ep, ct, cells, extents, ray_list, n_active, em,
+                                           kff, tsum, tcount,
                                            ln, ch, nchan, contsub, ln ? ln->dn_max : 0.0,
                                            tau_rrl, flux_rrl, (cudaStream_t)stream,
                                            (cudaStream_t)stream2));

@@ -30,6 +30,39 @@ fill_grid_kernel(const rjp_model m, uint8_t* __restrict__ nverts,
   const int ty0 = (t % tiles_y) * TY; t /= tiles_y;
   const int tx0 = m.x_lo + t * TX;
 
+  // Conservative whole-brick rejection (the jet fills < 1-15 % of the grid).  Every vertex
+  // v of the brick lies within R_b of the brick centre c, so w_v >= w_c - R_b and
+  // |r_v| <= |r_c| + R_b; the jet width w_0 rho(|r|)^eps grows with |r| (eps > 0), hence
+  // no vertex can pass the inside test if w_c - R_b > w_jet(|r_c| + R_b) (or if the whole
+  // brick is below the launch radius).  The 1e-6 margin dwarfs rounding, so the integer
+  // counts are unchanged: such bricks are all zeros and are written without any test.
+  bool skip = false;
+  if (m.eps > 0.0 && m.w0 > 0.0) {
+    const double hx = 0.5 * TX * m.cs, hy = 0.5 * TY * m.cs, hz = 0.5 * TZ * m.cs;
+    const Rw c = xyz_to_rw(m, corner(m.cs, tx0, m.nx) + hx, corner(m.cs, ty0, m.ny) + hy,
+                           corner(m.cs, tz0, m.nz) + hz);
+    const double rb = sqrt(hx * hx + hy * hy + hz * hz) * (1.0 + 1e-9);
+    const double rmax = fabs(c.r) + rb;
+    if (rmax < m.r0 * (1.0 - 1e-9)) {
+      skip = true;
+    } else {
+      const double rh = rho_of(m, rmax);
+      if (rh > 0.0) skip = (c.w - rb) > m.w0 * pow(rh, m.eps) * (1.0 + 1e-6);
+    }
+  }
+  if (skip) {
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+    for (int lx = 0; lx < TX; ++lx) {
+      const int ix = tx0 + lx, iy = ty0 + wrp, iz = tz0 + lane;
+      if (ix >= m.x_hi || iy >= m.ny || iz >= m.nz) continue;
+      const size_t idx = ((size_t)(ix - m.x_lo) * m.ny + iy) * m.nz + iz;
+      nverts[idx] = 0;
+      reinterpret_cast<double2*>(cells)[idx] = make_double2(0.0, 0.0);
+    }
+    return;
+  }
+
   for (int v = threadIdx.x; v < NVERT; v += FILL_THREADS) {
     const int lz = v % (TZ + 1);
     const int ly = (v / (TZ + 1)) % (TY + 1);

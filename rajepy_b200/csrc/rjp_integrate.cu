@@ -9,15 +9,17 @@
 // memory -- no atomics, deterministic order.  HBM-bound.
 //
 // K4 `integrate_line_kernel` -- the channel loop: fp64-pipe bound, so it is shaped for
-// the math, not for streaming.  The fill recorded, per ray, the y-extent [y_lo, y_hi)
-// of its in-jet cells; a CTA owns ZTr adjacent rays and NG groups of 8 channels,
-// thread (g, r) accumulates tau_L of channels 8g..8g+7 of ray r in REGISTERS while it
-// walks the ray's extent.  Channel-independent factors of a cell (burst factor, Doppler
-// shift, widths, amplitude) are computed once by one thread and shared through a small
-// shared-memory list.  Cells outside the extents are never touched, so K4 re-reads only
-// the in-jet cells (< 1 % of the grid); rays that miss the jet just write 0 / NaN.
-// K3 and K4 are independent and are launched on two streams so that the HBM-bound sweep
-// overlaps the compute-bound channel loop.
+// the math, not for streaming.  The fill recorded, per ray, the y-extent [y_lo, y_hi) of
+// its in-jet cells and the list of rays that cross the jet at all.  One CTA owns ONE such
+// ray; thread g owns channels 8g..8g+7 and keeps their tau_L in REGISTERS while the CTA
+// walks the ray's extent: the threads each prepare one cell (burst factor, Doppler shift,
+// widths, amplitude -> shared-memory entry), then every thread adds all prepared cells
+// to its channels.  All lanes of a warp work on the same cell list (no divergence), rays
+// of different length never wait for each other, and the hardware scheduler balances
+// the ~5 % of rays that carry all the work.  The cubes are first filled with 0 / NaN
+// (rays that miss the jet) by a plain streaming kernel.  K4 re-reads only the in-jet
+// cells (< 1 % of the grid).  K3 and (prefill -> K4) are independent and are launched on
+// two streams so that the HBM-bound sweep overlaps the compute-bound channel loop.
 #include "rjp_device.cuh"
 
 namespace rjp {
@@ -266,37 +268,60 @@ __device__ __forceinline__ double planck_factor(const LineEntry& e, double dn) {
   return e.p0 + (1.0 - e.p0) * (-expm1(-e.hk * dn));
 }
 
-__global__ void __launch_bounds__(LINE_THREADS, 2)
+__global__ void prefill_cubes_kernel(double* __restrict__ tau, double* __restrict__ flux,
+                                     size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const double nanv = dnan();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (tau) tau[i] = 0.0;
+    if (flux) flux[i] = nanv;
+  }
+}
+
+__global__ void ray_list_kernel(const int2* __restrict__ extents, int nray,
+                                int32_t* __restrict__ list, int32_t* __restrict__ n_active) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool on = false;
+  if (i < nray) {
+    const int2 e = extents[i];
+    on = e.x < e.y;
+  }
+  // warp-aggregated append
+  const unsigned m = __ballot_sync(0xffffffffu, on);
+  if (m == 0u) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(n_active, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (on) list[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
+
+#ifndef RJP_LINE_MINB
+#define RJP_LINE_MINB 1
+#endif
+__global__ void __launch_bounds__(LINE_THREADS, RJP_LINE_MINB)
 integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
                       const rjp_line ln, const rjp_channels ch, const int nchan,
-                      const int contsub, const int ng_log2, const double dn_max,
-                      const double2* __restrict__ cells,
-                      const int2* __restrict__ extents, double* __restrict__ tau_rrl,
+                      const int contsub, const double dn_max,
+                      const double2* __restrict__ cells, const int2* __restrict__ extents,
+                      const int32_t* __restrict__ ray_list, double* __restrict__ tau_rrl,
                       double* __restrict__ flux_rrl) {
   __shared__ Params s_p;
   __shared__ rjp_line s_ln;
   __shared__ LineEntry s_list[LINE_THREADS];
-  __shared__ double s_part[3][LINE_THREADS];
+  __shared__ double s_part[2][LINE_THREADS];
   __shared__ int s_pcnt[LINE_THREADS];
   stage_params(&s_p, m, ep);
   if (threadIdx.x == 0) s_ln = ln;
 
-  const int NG = 1 << ng_log2;              // channel groups per ray
-  const int ZTr = blockDim.x >> ng_log2;    // rays per CTA
-  const int t = threadIdx.x;
-  const int r = t & (ZTr - 1), g = t / ZTr;
-  const int ztiles = (m.nz + ZTr - 1) / ZTr;
-  const int xl = blockIdx.x / ztiles;
-  const int iz = (blockIdx.x % ztiles) * ZTr + r;
-  const bool active = iz < m.nz;
+  const int NT = blockDim.x;
+  const int g = threadIdx.x;
+  const int ray = ray_list[blockIdx.x];          // slab-local ray index = xl * nz + iz
+  const int xl = ray / m.nz, iz = ray - xl * m.nz;
   const int ix = m.x_lo + xl;
-  const int nxs = m.x_hi - m.x_lo;
-  const size_t pix = (size_t)xl * m.nz + (active ? iz : 0);
-  const size_t plane = (size_t)nxs * m.nz;
+  const size_t plane = (size_t)(m.x_hi - m.x_lo) * m.nz;
+  const int2 ext = extents[ray];
 
-  int2 ext = make_int2(0, 0);
-  if (active) ext = extents[pix];
-  if (ext.x >= ext.y) ext = make_int2(0, 0);  // ray misses the jet
   const int k0 = g * GCH;
   double dn[GCH];
 #pragma unroll
@@ -305,69 +330,67 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
 #pragma unroll
   for (int j = 0; j < GCH; ++j) acc[j] = 0.0;
   ContAcc ca = {0.0, 0.0, 0.0, 0};
-  const Ray ray = ray_of(s_p.m, ix, active ? iz : 0);
-  const double2* col = cells + (size_t)xl * m.ny * m.nz + (active ? iz : 0);
+  const Ray rc = ray_of(s_p.m, ix, iz);
+  const double2* col = cells + (size_t)xl * m.ny * m.nz + iz;
   __syncthreads();
 
-  for (int y0 = ext.x; __syncthreads_or(y0 < ext.y); y0 += NG) {
-    // phase 1: the ray's NG threads each prepare one cell of the extent
+  for (int y0 = ext.x; y0 < ext.y; y0 += NT) {
+    // phase 1: every thread prepares one cell of the extent
     const int iy = y0 + g;
     LineEntry e;
     e.amp = 0.0;
     if (iy < ext.y) {
       const double2 c = col[(size_t)iy * m.nz];
       if (!empty_cell(c)) {
-        const Decoded d = decode(c, s_p, ray, ix, iy, iz);
+        const Decoded d = decode(c, s_p, rc, ix, iy, iz);
         accumulate(ca, d, ct.t_exponent);
         if (d.ne_ok && d.t_ok) e = make_entry(d, s_p.m, s_ln, dn_max, ix, iy, iz);
       }
     }
-    s_list[r * NG + g] = e;
+    s_list[g] = e;
     __syncthreads();
-    // phase 2: thread (g, r) adds every cell of ray r to its 8 channels
-    const int n = min(NG, ext.y - y0);
-    for (int i = 0; i < n; ++i) {
-      const LineEntry en = s_list[r * NG + i];
-      if (en.amp == 0.0) continue;
+    // phase 2: every thread adds all prepared cells to its 8 channels
+    const int n = min(NT, ext.y - y0);
+    if (k0 < nchan) {
+      for (int i = 0; i < n; ++i) {
+        const LineEntry en = s_list[i];
+        if (en.amp == 0.0) continue;
+#pragma unroll 1
+        for (int h = 0; h < GCH; h += 4) {
+          double x[4], w[4];
 #pragma unroll
-      for (int h = 0; h < GCH; h += 4) {
-        double x[4], w[4];
+          for (int j = 0; j < 4; ++j) x[j] = fma(dn[h + j], en.inv_s2, en.xs);
+          faddeeva_re_n<4>(x, en.y, w);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) x[j] = fma(dn[h + j], en.inv_s2, en.xs);
-        faddeeva_re_n<4>(x, en.y, w);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          acc[h + j] += en.amp * w[j] * planck_factor(en, dn[h + j]);
+          for (int j = 0; j < 4; ++j)
+            acc[h + j] += en.amp * w[j] * planck_factor(en, dn[h + j]);
+        }
       }
     }
+    __syncthreads();
   }
 
-  // per-ray continuum sums (needed by the flux epilogue): reduce the NG partials of ray r
+  // the ray's continuum sums (needed by the flux epilogue): reduce the NT partials
+  s_part[0][g] = ca.kff;
+  s_part[1][g] = ca.tsum;
+  s_pcnt[g] = ca.cnt;
+  __syncthreads();
   double kray = 0.0, ts = 0.0;
   int cn = 0;
-  if (__syncthreads_or(ext.x < ext.y)) {  // some ray of this tile crosses the jet
-    s_part[0][r * NG + g] = ca.kff;
-    s_part[1][r * NG + g] = ca.tsum;
-    s_pcnt[r * NG + g] = ca.cnt;
-    __syncthreads();
-    if (ext.x < ext.y) {
-      for (int i = 0; i < NG; ++i) {
-        kray += s_part[0][r * NG + i];
-        ts += s_part[1][r * NG + i];
-        cn += s_pcnt[r * NG + i];
-      }
-    }
-    kray *= ct.tau_scale;
+  for (int i = 0; i < NT; ++i) {
+    kray += s_part[0][i];
+    ts += s_part[1][i];
+    cn += s_pcnt[i];
   }
-  if (!active) return;
+  kray *= ct.tau_scale;
 
   // K5 epilogue: rrls.py:444-447, physics.py:571-574, classes.py:1323-1328, :1484-1488
-  const double tmean = ts / (double)cn;  // NaN for rays that miss the jet
+  const double tmean = ts / (double)cn;
 #pragma unroll
   for (int j = 0; j < GCH; ++j) {
     const int c = k0 + j;
     if (c >= nchan) break;
-    if (tau_rrl) tau_rrl[(size_t)c * plane + pix] = acc[j];
+    if (tau_rrl) tau_rrl[(size_t)c * plane + ray] = acc[j];
     if (flux_rrl) {
       double s = dnan();
       if (cn > 0) {
@@ -377,7 +400,7 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
         s = bnu * ec * (1.0 - exp(-acc[j]));
         if (!contsub) s += __ldg(ch.aff + c) * (tmean * (1.0 - ec));
       }
-      flux_rrl[(size_t)c * plane + pix] = s;
+      flux_rrl[(size_t)c * plane + ray] = s;
     }
   }
 }
@@ -412,10 +435,20 @@ __global__ void continuum_images_kernel(const double* __restrict__ kff,
 
 using namespace rjp;
 
+extern "C" int rjp_launch_ray_list(const int32_t* extents, int nray, int32_t* list,
+                                   int32_t* n_active, cudaStream_t stream) {
+  if (nray <= 0) return RJP_OK;
+  cudaMemsetAsync(n_active, 0, sizeof(int32_t), stream);
+  ray_list_kernel<<<(nray + 255) / 256, 256, 0, stream>>>(
+      reinterpret_cast<const int2*>(extents), nray, list, n_active);
+  return RJP_OK;
+}
+
 extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
                                     const rjp_continuum* ct, const rjp_cell* cells,
-                                    const int32_t* extents, double* em, double* kff,
-                                    double* tsum, int32_t* tcount, const rjp_line* ln,
+                                    const int32_t* extents, const int32_t* ray_list,
+                                    int n_active, double* em, double* kff, double* tsum,
+                                    int32_t* tcount, const rjp_line* ln,
                                     const rjp_channels* ch, int nchan, int contsub,
                                     double dn_max, double* tau_rrl, double* flux_rrl,
                                     cudaStream_t stream, cudaStream_t stream2) {
@@ -438,24 +471,20 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
   integrate_continuum_kernel<<<(unsigned)ctas, 256, 0, stream>>>(*m, *ep, *ct, c4, em, kff,
                                                                 tsum, tcount);
   if (lines) {
+    const size_t ncube = (size_t)nchan * nxs * m->nz;
+    prefill_cubes_kernel<<<148 * 8, 256, 0, ls>>>(tau_rrl, flux_rrl, ncube);
     // channel blocks of at most 8 * 256 channels per launch
-    for (int c0 = 0; c0 < nchan; c0 += GCH * LINE_THREADS) {
+    for (int c0 = 0; c0 < nchan && n_active > 0; c0 += GCH * LINE_THREADS) {
       const int nc = (nchan - c0 < GCH * LINE_THREADS) ? nchan - c0 : GCH * LINE_THREADS;
       const int groups = (nc + GCH - 1) / GCH;
-      int ng_log2 = 0;
-      while ((1 << ng_log2) < groups) ++ng_log2;
-      int ztr = LINE_THREADS >> ng_log2;
-      if (ztr > 32) ztr = 32;
-      const int threads = ztr << ng_log2;
-      const long long tiles = (long long)nxs * ((m->nz + ztr - 1) / ztr);
-      if (tiles > 2147483647LL) return RJP_ERR_ARG;
+      const int threads = ((groups + 31) / 32) * 32;
       rjp_channels cb = *ch;
       cb.dnu += c0; cb.nu += c0; cb.cff += c0; cb.aff += c0; cb.bnu += c0;
       const size_t off = (size_t)c0 * nxs * m->nz;
-      integrate_line_kernel<<<(unsigned)tiles, threads, 0, ls>>>(
-          *m, *ep, *ct, *ln, cb, nc, contsub, ng_log2, dn_max, c4,
-          reinterpret_cast<const int2*>(extents), tau_rrl ? tau_rrl + off : nullptr,
-          flux_rrl ? flux_rrl + off : nullptr);
+      integrate_line_kernel<<<(unsigned)n_active, threads, 0, ls>>>(
+          *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4,
+          reinterpret_cast<const int2*>(extents), ray_list,
+          tau_rrl ? tau_rrl + off : nullptr, flux_rrl ? flux_rrl + off : nullptr);
     }
   }
   if (fork) {

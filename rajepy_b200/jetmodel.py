@@ -522,11 +522,27 @@ class JetModel:
                          "n_ties": n_ties, "n_patched": 0}
             if n_ties > 0:
                 self._resolve_ties(ties[:n_ties].cpu().numpy().astype(np.int64))
+            self._build_ray_list()
         if self.log:
             self.log.add_entry(mtype="INFO",
                                entry=_time.strftime('Finished in %Hh%Mm%Ss',
                                                     _time.gmtime(_time.time() - t0)))
         return self._dev
+
+    def _build_ray_list(self):
+        """Rays that cross the jet: the channel loop runs one CTA per listed ray."""
+        torch = _torch()
+        lib = _cabi.load()
+        d = self._dev
+        nray = d["extents"].shape[0]
+        rays = torch.empty(nray, dtype=torch.int32, device=d["device"])
+        n_act = torch.zeros(1, dtype=torch.int32, device=d["device"])
+        st = lib.rjp_ray_list(d["extents"].data_ptr(), nray, rays.data_ptr(),
+                              n_act.data_ptr(), self._stream())
+        _cabi.check(st, "rjp_ray_list")
+        _launched()
+        d["n_active"] = int(n_act.item())
+        d["rays"] = rays[:max(d["n_active"], 1)].clone()
 
     def _resolve_ties(self, ties):
         """Vertices whose inside test the device could not call: decide every
@@ -793,9 +809,10 @@ class JetModel:
             tau = flux = None
             if line is None:
                 st = lib.rjp_integrate(d["model"], ep, ct, d["cells"].data_ptr(),
-                                       d["extents"].data_ptr(), em.data_ptr(),
-                                       kff.data_ptr(), tsum.data_ptr(), cnt.data_ptr(), None,
-                                       None, 0, 1, None, None, self._stream(), None)
+                                       d["extents"].data_ptr(), d["rays"].data_ptr(),
+                                       d["n_active"], em.data_ptr(), kff.data_ptr(),
+                                       tsum.data_ptr(), cnt.data_ptr(), None, None, 0, 1,
+                                       None, None, self._stream(), None)
             else:
                 ln, chans, keep = self._line_structs(line, freqs, dev)
                 nch = len(freqs)
@@ -804,15 +821,16 @@ class JetModel:
                 if want_flux:
                     flux = torch.empty((nch, nxs, nz), dtype=torch.float64, device=dev)
                 st = lib.rjp_integrate(d["model"], ep, ct, d["cells"].data_ptr(),
-                                       d["extents"].data_ptr(), em.data_ptr(),
-                                       kff.data_ptr(), tsum.data_ptr(), cnt.data_ptr(), ln,
+                                       d["extents"].data_ptr(), d["rays"].data_ptr(),
+                                       d["n_active"], em.data_ptr(), kff.data_ptr(),
+                                       tsum.data_ptr(), cnt.data_ptr(), ln,
                                        chans, nch, 1 if contsub else 0,
                                        tau.data_ptr() if want_tau else None,
                                        flux.data_ptr() if want_flux else None,
                                        self._stream(), d["stream2"].cuda_stream)
                 del keep
             _cabi.check(st, "rjp_integrate")
-            _launched(1 if line is None else 1 + (len(freqs) + 2047) // 2048)
+            _launched(1 if line is None else 2 + (len(freqs) + 2047) // 2048)
         self._cont = {"key": key_c, "em": em, "kff": kff, "tsum": tsum, "cnt": cnt}
         if line is None:
             return self._cont
