@@ -285,24 +285,25 @@ __device__ __forceinline__ double faddeeva_re(double x, double y) {
   return 2.0 * (pr * u2r - pi * u2i) + ur * 0.56418958354775628695;  // 1/sqrt(pi)
 }
 
-// 1/d for d in [L^2, 1e300): float seed + two Newton steps (no special cases to handle;
-// the result is within 1 ulp, which is all the rational approximation needs).
+// 1/d for finite positive d: MUFU.RCP64H seed (rcp.approx.ftz.f64, ~20 bits over the whole
+// double range) + two Newton steps; within 1 ulp, no special cases needed here.
 __device__ __forceinline__ double rcp_pos(double d) {
-  double r = (double)__frcp_rn((float)d);
-  r = r * fma(-d, r, 2.0);          // 2^-24 -> 2^-48
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = r * fma(-d, r, 2.0);          // 2^-20 -> 2^-40
   r = fma(r, fma(-d, r, 1.0), r);   // -> rounding-limited
   return r;
 }
 
-// The same for NV independent arguments sharing y: the NV recurrences are interleaved
-// so that the fp64 pipe always has independent FMAs in flight.
+// NV independent arguments (x_v, y_v): the NV recurrences are interleaved so that the
+// fp64 pipe always has independent FMAs in flight (DFMA latency ~8.5 cycles on B200).
 template <int NV>
-__device__ __forceinline__ void faddeeva_re_n(const double* x, double y, double* out) {
+__device__ __forceinline__ void faddeeva_re_n(const double* x, const double* y, double* out) {
   const double L = RJP_WEIDEMAN_L;
-  const double dr = L + y, nr = L - y;
   double inv[NV], s[NV], q[NV], zr[NV], zi[NV], b1[NV], b2[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
+    const double dr = L + y[v], nr = L - y[v];
     inv[v] = rcp_pos(fma(x[v], x[v], dr * dr));
     zr[v] = (nr * dr - x[v] * x[v]) * inv[v];
     zi[v] = (2.0 * L) * x[v] * inv[v];
@@ -322,11 +323,37 @@ __device__ __forceinline__ void faddeeva_re_n(const double* x, double y, double*
   }
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
+    const double dr = L + y[v];
     const double pr = c_weideman[RJP_WEIDEMAN_N - 1] + zr[v] * b1[v] - q[v] * b2[v];
     const double pi = zi[v] * b1[v];
     const double ur = dr * inv[v], ui = x[v] * inv[v];
     const double u2r = ur * ur - ui * ui, u2i = 2.0 * ur * ui;
     out[v] = 2.0 * (pr * u2r - pi * u2i) + ur * 0.56418958354775628695;
+  }
+}
+
+// Line wings, |z|^2 >= 64: six levels of the Laplace continued fraction
+// w = (i/sqrt(pi)) / (z - (1/2)/(z - 1/(z - (3/2)/(z - ...)))) collapsed into
+// (i/sqrt(pi)) p(u) / (z q(u)), u = z^2 (tools/gen_laplace_cf.py).  Re w to <= 3e-10
+// relative against wofz for |z| >= 8 at half the cost of the rational approximation above.
+template <int NV>
+__device__ __forceinline__ void faddeeva_wing_n(const double* x, const double* y, double* out) {
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const double ur = fma(x[v], x[v], -y[v] * y[v]), ui = 2.0 * x[v] * y[v];
+    // p(u) = ((u - 10) u + 21.75) u - 6
+    double ar = ur - 10.0, ai = ui, t;
+    t = fma(ar, ur, fma(-ai, ui, 21.75)); ai = fma(ar, ui, ai * ur); ar = t;
+    t = fma(ar, ur, fma(-ai, ui, -6.0)); ai = fma(ar, ui, ai * ur); ar = t;
+    // q(u) = ((u - 10.5) u + 26.25) u - 13.125
+    double qr = ur - 10.5, qi = ui;
+    t = fma(qr, ur, fma(-qi, ui, 26.25)); qi = fma(qr, ui, qi * ur); qr = t;
+    t = fma(qr, ur, fma(-qi, ui, -13.125)); qi = fma(qr, ui, qi * ur); qr = t;
+    // B = z q(u);  Re w = (A_r B_i - A_i B_r) / (sqrt(pi) |B|^2)
+    const double br = fma(x[v], qr, -y[v] * qi), bi = fma(x[v], qi, y[v] * qr);
+    const double num = fma(ar, bi, -ai * br);
+    const double den = fma(br, br, bi * bi);
+    out[v] = 0.56418958354775628695 * num * rcp_pos(den);
   }
 }
 

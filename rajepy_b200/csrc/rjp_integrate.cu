@@ -16,10 +16,10 @@
 // widths, amplitude -> shared-memory entry), then every thread adds all prepared cells
 // to its channels.  All lanes of a warp work on the same cell list (no divergence), rays
 // of different length never wait for each other, and the hardware scheduler balances
-// the ~5 % of rays that carry all the work.  The cubes are first filled with 0 / NaN
-// (rays that miss the jet) by a plain streaming kernel.  K4 re-reads only the in-jet
-// cells (< 1 % of the grid).  K3 and (prefill -> K4) are independent and are launched on
-// two streams so that the HBM-bound sweep overlaps the compute-bound channel loop.
+// the ~5 % of rays that carry all the work.  Rays that miss the jet get 0 / NaN from a
+// plain streaming kernel.  K4 re-reads only the in-jet cells (< 1 % of the grid).  The
+// memory-bound kernels (K3, missed rays) and K4 are independent and are launched on two
+// streams so that the HBM-bound work overlaps the compute-bound channel loop.
 #include "rjp_device.cuh"
 
 namespace rjp {
@@ -198,7 +198,8 @@ __device__ __forceinline__ void reduce_and_store(ContAcc a, const rjp_continuum&
 }
 
 // ------------------------------------------------------------------ continuum only
-__global__ void __launch_bounds__(256, 2)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 integrate_continuum_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
                            const double2* __restrict__ cells, double* __restrict__ em,
                            double* __restrict__ kff, double* __restrict__ tsum,
@@ -268,11 +269,18 @@ __device__ __forceinline__ double planck_factor(const LineEntry& e, double dn) {
   return e.p0 + (1.0 - e.p0) * (-expm1(-e.hk * dn));
 }
 
-__global__ void prefill_cubes_kernel(double* __restrict__ tau, double* __restrict__ flux,
-                                     size_t n) {
+// Rays that miss the jet: tau_L = 0, flux = NaN in every channel (nansum / nanmean of an
+// all-NaN column).  Pure streaming writes; rays that cross the jet are
+// left to the channel loop, so the two kernels can run concurrently in any order.
+__global__ void fill_missed_rays_kernel(const int2* __restrict__ extents, size_t nray,
+                                        int nchan, double* __restrict__ tau,
+                                        double* __restrict__ flux) {
+  const size_t n = nray * (size_t)nchan;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const double nanv = dnan();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int2 e = __ldg(extents + (i % nray));
+    if (e.x < e.y) continue;
     if (tau) tau[i] = 0.0;
     if (flux) flux[i] = nanv;
   }
@@ -296,10 +304,8 @@ __global__ void ray_list_kernel(const int2* __restrict__ extents, int nray,
   if (on) list[base + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
-#ifndef RJP_LINE_MINB
-#define RJP_LINE_MINB 1
-#endif
-__global__ void __launch_bounds__(LINE_THREADS, RJP_LINE_MINB)
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
                       const rjp_line ln, const rjp_channels ch, const int nchan,
                       const int contsub, const double dn_max,
@@ -308,24 +314,28 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
                       double* __restrict__ flux_rrl) {
   __shared__ Params s_p;
   __shared__ rjp_line s_ln;
-  __shared__ LineEntry s_list[LINE_THREADS];
+  __shared__ LineEntry s_list[LINE_THREADS + 4];
   __shared__ double s_part[2][LINE_THREADS];
   __shared__ int s_pcnt[LINE_THREADS];
+  __shared__ int s_woff[LINE_THREADS / 32 + 1];
   stage_params(&s_p, m, ep);
   if (threadIdx.x == 0) s_ln = ln;
 
   const int NT = blockDim.x;
-  const int g = threadIdx.x;
+  const int g = threadIdx.x, lane = g & 31, wrp = g >> 5, nwarps = NT >> 5;
   const int ray = ray_list[blockIdx.x];          // slab-local ray index = xl * nz + iz
   const int xl = ray / m.nz, iz = ray - xl * m.nz;
   const int ix = m.x_lo + xl;
   const size_t plane = (size_t)(m.x_hi - m.x_lo) * m.nz;
   const int2 ext = extents[ray];
 
-  const int k0 = g * GCH;
+  // thread g owns channels g, g + NT, g + 2 NT, ...: at every step the lanes of a warp hold
+  // 32 neighbouring channels, i.e. nearly the same point of the line profile, so the
+  // core / wing branch below is warp-uniform
   double dn[GCH];
 #pragma unroll
-  for (int j = 0; j < GCH; ++j) dn[j] = (k0 + j < nchan) ? __ldg(ch.dnu + k0 + j) : 0.0;
+  for (int j = 0; j < GCH; ++j)
+    dn[j] = (g + j * NT < nchan) ? __ldg(ch.dnu + g + j * NT) : 0.0;
   double acc[GCH];
 #pragma unroll
   for (int j = 0; j < GCH; ++j) acc[j] = 0.0;
@@ -335,7 +345,8 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   __syncthreads();
 
   for (int y0 = ext.x; y0 < ext.y; y0 += NT) {
-    // phase 1: every thread prepares one cell of the extent
+    // phase 1: every thread prepares one cell of the extent; cells that emit no line
+    // are dropped by an ordered compaction (deterministic summation order)
     const int iy = y0 + g;
     LineEntry e;
     e.amp = 0.0;
@@ -347,25 +358,47 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
         if (d.ne_ok && d.t_ok) e = make_entry(d, s_p.m, s_ln, dn_max, ix, iy, iz);
       }
     }
-    s_list[g] = e;
+    const bool keep = e.amp != 0.0;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_woff[wrp] = __popc(bal);
     __syncthreads();
-    // phase 2: every thread adds all prepared cells to its 8 channels
-    const int n = min(NT, ext.y - y0);
-    if (k0 < nchan) {
-      for (int i = 0; i < n; ++i) {
-        const LineEntry en = s_list[i];
-        if (en.amp == 0.0) continue;
+    int base = 0, n = 0;
+    for (int w = 0; w < nwarps; ++w) {
+      if (w < wrp) base += s_woff[w];
+      n += s_woff[w];
+    }
+    if (keep) s_list[base + __popc(bal & ((1u << lane) - 1u))] = e;
+    __syncthreads();
+    if (g < 3 && n > 0) {  // pad the last batch of 4 with zero-amplitude copies
+      LineEntry pad = s_list[n - 1];
+      pad.amp = 0.0;
+      s_list[n + g] = pad;
+    }
+    __syncthreads();
+
+    // phase 2: every thread adds all prepared cells to its channels, 4 cells at a time
+    // (channel loop outermost: the running sum and the channel offset stay in registers)
 #pragma unroll 1
-        for (int h = 0; h < GCH; h += 4) {
-          double x[4], w[4];
+    for (int j = 0; j < GCH; ++j) {
+      if (g + j * NT >= nchan) break;
+      const double dnj = dn[j];
+      double sum = 0.0;
+      for (int i = 0; i < n; i += 4) {
+        const LineEntry* eb = s_list + i;
+        double x[4], yy[4], w[4];
+        bool wing = true;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) x[j] = fma(dn[h + j], en.inv_s2, en.xs);
-          faddeeva_re_n<4>(x, en.y, w);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            acc[h + j] += en.amp * w[j] * planck_factor(en, dn[h + j]);
+        for (int v = 0; v < 4; ++v) {
+          x[v] = fma(dnj, eb[v].inv_s2, eb[v].xs);
+          yy[v] = eb[v].y;
+          wing = wing && (fma(x[v], x[v], yy[v] * yy[v]) >= 64.0);
         }
+        if (wing) faddeeva_wing_n<4>(x, yy, w);
+        else faddeeva_re_n<4>(x, yy, w);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) sum = fma(eb[v].amp * w[v], planck_factor(eb[v], dnj), sum);
       }
+      acc[j] += sum;
     }
     __syncthreads();
   }
@@ -388,7 +421,7 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   const double tmean = ts / (double)cn;
 #pragma unroll
   for (int j = 0; j < GCH; ++j) {
-    const int c = k0 + j;
+    const int c = g + j * NT;
     if (c >= nchan) break;
     if (tau_rrl) tau_rrl[(size_t)c * plane + ray] = acc[j];
     if (flux_rrl) {
@@ -468,11 +501,12 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
     cudaStreamWaitEvent(stream2, fork, 0);
     ls = stream2;
   }
-  integrate_continuum_kernel<<<(unsigned)ctas, 256, 0, stream>>>(*m, *ep, *ct, c4, em, kff,
-                                                                tsum, tcount);
+  integrate_continuum_kernel<2><<<(unsigned)ctas, 256, 0, stream>>>(*m, *ep, *ct, c4, em, kff,
+                                                                   tsum, tcount);
   if (lines) {
-    const size_t ncube = (size_t)nchan * nxs * m->nz;
-    prefill_cubes_kernel<<<148 * 8, 256, 0, ls>>>(tau_rrl, flux_rrl, ncube);
+    // memory-bound work (dense sweep, missed rays) on `stream`, the channel loop beside it
+    fill_missed_rays_kernel<<<148 * 8, 256, 0, stream>>>(
+        reinterpret_cast<const int2*>(extents), (size_t)nxs * m->nz, nchan, tau_rrl, flux_rrl);
     // channel blocks of at most 8 * 256 channels per launch
     for (int c0 = 0; c0 < nchan && n_active > 0; c0 += GCH * LINE_THREADS) {
       const int nc = (nchan - c0 < GCH * LINE_THREADS) ? nchan - c0 : GCH * LINE_THREADS;
@@ -481,10 +515,20 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
       rjp_channels cb = *ch;
       cb.dnu += c0; cb.nu += c0; cb.cff += c0; cb.aff += c0; cb.bnu += c0;
       const size_t off = (size_t)c0 * nxs * m->nz;
-      integrate_line_kernel<<<(unsigned)n_active, threads, 0, ls>>>(
-          *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4,
-          reinterpret_cast<const int2*>(extents), ray_list,
-          tau_rrl ? tau_rrl + off : nullptr, flux_rrl ? flux_rrl + off : nullptr);
+      const int2* ex2 = reinterpret_cast<const int2*>(extents);
+      double* t_out = tau_rrl ? tau_rrl + off : nullptr;
+      double* f_out = flux_rrl ? flux_rrl + off : nullptr;
+      // 128 registers per thread at every block size (measured best on B200: 8 CTAs of 64
+      // threads per SM; see profiles/README.md)
+      if (threads <= 64)
+        integrate_line_kernel<64, 8><<<(unsigned)n_active, threads, 0, ls>>>(
+            *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, t_out, f_out);
+      else if (threads <= 128)
+        integrate_line_kernel<128, 4><<<(unsigned)n_active, threads, 0, ls>>>(
+            *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, t_out, f_out);
+      else
+        integrate_line_kernel<LINE_THREADS, 2><<<(unsigned)n_active, threads, 0, ls>>>(
+            *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, t_out, f_out);
     }
   }
   if (fork) {

@@ -1080,6 +1080,8 @@ class JetModel:
 def _to_host(t):
     """Device tensor -> numpy through a pinned staging buffer."""
     torch = _torch()
+    if hasattr(t, "to_host"):          # folded all-gather view (sharding._FoldedView)
+        return t.to_host().numpy()
     if t.device.type != "cuda":
         return t.contiguous().numpy()
     t = t.contiguous()

@@ -34,8 +34,11 @@ def _worker(rank, world, port, nx, img_path, out_dir):
     full_img = sharding.gather_x(img, nx, rank, world, dim=0)
     full_cube = sharding.gather_x(cube, nx, rank, world, dim=1)
     full_cnt = sharding.gather_x(cnt, nx, rank, world, dim=0)
+    host_cube = full_cube.to_host() if hasattr(full_cube, "to_host") else full_cube
+    assert tuple(full_cube.shape) == (cube.shape[0], nx, cube.shape[2])
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), img=full_img.numpy(),
-             cube=full_cube.numpy(), cnt=full_cnt.numpy())
+             cube=host_cube.numpy(), cnt=full_cnt.numpy(),
+             cube0=full_cube[0].numpy() if hasattr(full_cube, "to_host") else full_cube[0].numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -61,6 +64,7 @@ def test_gather_x_world2(nx_case):
         out = np.load(os.path.join(tmp, f"r{r}.npz"))
         assert np.array_equal(out["img"], em)
         assert np.array_equal(out["cube"], tau)
+        assert np.array_equal(out["cube0"], tau[0])
         assert np.array_equal(out["cnt"], cnt)
 
 
