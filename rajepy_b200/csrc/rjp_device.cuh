@@ -332,9 +332,9 @@ __device__ __forceinline__ void faddeeva_re_n(const double* x, const double* y, 
   }
 }
 
-// Line wings, |z|^2 >= 64: six levels of the Laplace continued fraction
+// Line wings, |z|^2 >= 36: six levels of the Laplace continued fraction
 // w = (i/sqrt(pi)) / (z - (1/2)/(z - 1/(z - (3/2)/(z - ...)))) collapsed into
-// (i/sqrt(pi)) p(u) / (z q(u)), u = z^2 (tools/gen_laplace_cf.py).  Re w to <= 3e-10
+// (i/sqrt(pi)) p(u) / (z q(u)), u = z^2 (tools/gen_laplace_cf.py).  Re w to <= 2.1e-8 (|z| >= 6; 3e-10 for |z| >= 8)
 // relative against wofz for |z| >= 8 at half the cost of the rational approximation above.
 template <int NV>
 __device__ __forceinline__ void faddeeva_wing_n(const double* x, const double* y, double* out) {

@@ -36,20 +36,27 @@ fill_grid_kernel(const rjp_model m, uint8_t* __restrict__ nverts,
   // no vertex can pass the inside test if w_c - R_b > w_jet(|r_c| + R_b) (or if the whole
   // brick is below the launch radius).  The 1e-6 margin dwarfs rounding, so the integer
   // counts are unchanged: such bricks are all zeros and are written without any test.
-  bool skip = false;
-  if (m.eps > 0.0 && m.w0 > 0.0) {
-    const double hx = 0.5 * TX * m.cs, hy = 0.5 * TY * m.cs, hz = 0.5 * TZ * m.cs;
-    const Rw c = xyz_to_rw(m, corner(m.cs, tx0, m.nx) + hx, corner(m.cs, ty0, m.ny) + hy,
-                           corner(m.cs, tz0, m.nz) + hz);
-    const double rb = sqrt(hx * hx + hy * hy + hz * hz) * (1.0 + 1e-9);
-    const double rmax = fabs(c.r) + rb;
-    if (rmax < m.r0 * (1.0 - 1e-9)) {
-      skip = true;
-    } else {
-      const double rh = rho_of(m, rmax);
-      if (rh > 0.0) skip = (c.w - rb) > m.w0 * pow(rh, m.eps) * (1.0 + 1e-6);
+  // (decided by one thread, broadcast through shared memory: the bound needs a pow)
+  __shared__ int s_skip;
+  if (threadIdx.x == 0) {
+    bool skip0 = false;
+    if (m.eps > 0.0 && m.w0 > 0.0) {
+      const double hx = 0.5 * TX * m.cs, hy = 0.5 * TY * m.cs, hz = 0.5 * TZ * m.cs;
+      const Rw c = xyz_to_rw(m, corner(m.cs, tx0, m.nx) + hx, corner(m.cs, ty0, m.ny) + hy,
+                             corner(m.cs, tz0, m.nz) + hz);
+      const double rb = sqrt(hx * hx + hy * hy + hz * hz) * (1.0 + 1e-9);
+      const double rmax = fabs(c.r) + rb;
+      if (rmax < m.r0 * (1.0 - 1e-9)) {
+        skip0 = true;
+      } else {
+        const double rh = rho_of(m, rmax);
+        if (rh > 0.0) skip0 = (c.w - rb) > m.w0 * pow(rh, m.eps) * (1.0 + 1e-6);
+      }
     }
+    s_skip = skip0 ? 1 : 0;
   }
+  __syncthreads();
+  const bool skip = s_skip != 0;
   if (skip) {
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
 #pragma unroll

@@ -391,7 +391,7 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
         for (int v = 0; v < 4; ++v) {
           x[v] = fma(dnj, eb[v].inv_s2, eb[v].xs);
           yy[v] = eb[v].y;
-          wing = wing && (fma(x[v], x[v], yy[v] * yy[v]) >= 64.0);
+          wing = wing && (fma(x[v], x[v], yy[v] * yy[v]) >= 36.0);
         }
         if (wing) faddeeva_wing_n<4>(x, yy, w);
         else faddeeva_re_n<4>(x, yy, w);
