@@ -438,6 +438,138 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   }
 }
 
+// ------------------------------------------------------------------ sweep beside the loop
+// Persistent, bulk-copy-staged form of the dense sweep for passes that also run the channel
+// loop.  A small grid (one 4-warp CTA per SM) is resident from the start and leaves most
+// of every SM to the compute-bound loop, so the two overlap instead of queueing behind
+// each other (the block scheduler drains one kernel's CTAs before the other's).  With
+// only four warps per SM the loads cannot live in registers: each warp streams its tile
+// (32 rays x all y) through a two-stage shared-memory ring filled by the TMA engine with
+// 1-D bulk copies (cp.async.bulk, one 512-byte z-row per copy, SWEEP_ROWS rows per stage,
+// completion on an mbarrier), i.e. 16 KB in flight per warp at no register cost.  Same
+// arithmetic as integrate_continuum_kernel, no cross-warp reduction; the warp also
+// writes 0 / NaN into the cubes for the rays of its tile that miss the jet.
+constexpr int SWEEP_ROWS = 16;
+constexpr int SWEEP_WARPS = 4;
+constexpr int SWEEP_STAGE_BYTES = SWEEP_ROWS * ZT * 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(SWEEP_WARPS * 32, 1)
+sweep_persistent_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
+                        const double2* __restrict__ cells, const int2* __restrict__ extents,
+                        double* __restrict__ em, double* __restrict__ kff,
+                        double* __restrict__ tsum, int32_t* __restrict__ tcount,
+                        const int nchan, double* __restrict__ tau_rrl,
+                        double* __restrict__ flux_rrl) {
+  extern __shared__ __align__(128) unsigned char sweep_smem[];
+  __shared__ Params s_p;
+  __shared__ __align__(8) unsigned long long s_bar[SWEEP_WARPS][2];
+  stage_params(&s_p, m, ep);
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  unsigned char* ring = sweep_smem + (size_t)wrp * 2 * SWEEP_STAGE_BYTES;
+  const uint32_t bar0 = smem_u32(&s_bar[wrp][0]), bar1 = smem_u32(&s_bar[wrp][1]);
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int ztiles = (m.nz + ZT - 1) / ZT;
+  const long long ntiles = (long long)(m.x_hi - m.x_lo) * ztiles;
+  const size_t plane = (size_t)(m.x_hi - m.x_lo) * m.nz;
+  const int nchunks = (m.ny + SWEEP_ROWS - 1) / SWEEP_ROWS;
+  uint32_t ph0 = 0, ph1 = 0;  // phase parity of the two stage barriers
+
+  for (long long tile = (long long)blockIdx.x * SWEEP_WARPS + wrp; tile < ntiles;
+       tile += (long long)gridDim.x * SWEEP_WARPS) {
+    const int xl = (int)(tile / ztiles);
+    const int z0 = (int)(tile % ztiles) * ZT;
+    const int iz = z0 + lane;
+    const int nlanes = min(ZT, m.nz - z0);          // rays of this tile
+    const bool active = lane < nlanes;
+    const uint32_t row_bytes = (uint32_t)nlanes * 16u;
+    const double2* base = cells + (size_t)xl * m.ny * m.nz + z0;
+    const int ix = m.x_lo + xl;
+    const Ray ray = ray_of(s_p.m, ix, active ? iz : z0);
+    ContAcc a = {0.0, 0.0, 0.0, 0};
+
+    // producer: lane 0 asks the TMA engine for the rows of chunk c into stage c & 1
+    auto issue = [&](int c) {
+      const int y0 = c * SWEEP_ROWS;
+      const int rows = min(SWEEP_ROWS, m.ny - y0);
+      const uint32_t bar = (c & 1) ? bar1 : bar0;
+      const uint32_t dst = smem_u32(ring + (size_t)(c & 1) * SWEEP_STAGE_BYTES);
+      mbar_expect_tx(bar, (uint32_t)rows * row_bytes);
+      for (int r = 0; r < rows; ++r)
+        bulk_g2s(dst + (uint32_t)r * (ZT * 16), base + (size_t)(y0 + r) * m.nz, row_bytes, bar);
+    };
+    if (lane == 0) {
+      issue(0);
+      if (nchunks > 1) issue(1);
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      const int st = c & 1;
+      if (st) { mbar_wait(bar1, ph1); ph1 ^= 1; } else { mbar_wait(bar0, ph0); ph0 ^= 1; }
+      const int y0 = c * SWEEP_ROWS;
+      const int rows = min(SWEEP_ROWS, m.ny - y0);
+      const double2* rowp = reinterpret_cast<const double2*>(ring + (size_t)st * SWEEP_STAGE_BYTES);
+      if (active) {
+        for (int r = 0; r < rows; ++r) {
+          const double2 cell = rowp[r * ZT + lane];
+          if (empty_cell(cell)) continue;
+          accumulate(a, decode(cell, s_p, ray, ix, y0 + r, iz), ct.t_exponent);
+        }
+      }
+      __syncwarp();
+      if (lane == 0 && c + 2 < nchunks) {
+        // the stage was read through the generic proxy: order that before the async writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(c + 2);
+      }
+    }
+    if (!active) continue;
+    const size_t pix = (size_t)xl * m.nz + iz;
+    em[pix] = a.em * ct.em_scale;
+    kff[pix] = a.kff * ct.tau_scale;
+    tsum[pix] = a.tsum;
+    tcount[pix] = a.cnt;
+    const int2 e = extents[pix];
+    if (e.x >= e.y) {  // the channel loop never visits this ray
+      const double nanv = dnan();
+      for (int c = 0; c < nchan; ++c) {
+        if (tau_rrl) tau_rrl[(size_t)c * plane + pix] = 0.0;
+        if (flux_rrl) flux_rrl[(size_t)c * plane + pix] = nanv;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ continuum images
 __global__ void continuum_images_kernel(const double* __restrict__ kff,
                                         const double* __restrict__ tsum,
@@ -501,12 +633,24 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
     cudaStreamWaitEvent(stream2, fork, 0);
     ls = stream2;
   }
-  integrate_continuum_kernel<2><<<(unsigned)ctas, 256, 0, stream>>>(*m, *ep, *ct, c4, em, kff,
-                                                                   tsum, tcount);
+  if (lines && fork && n_active > 0) {
+    // memory-bound work (dense sweep + missed rays) as a small persistent grid on `stream`,
+    // resident beside the channel loop on `stream2`
+    const int sweep_smem_bytes = SWEEP_WARPS * 2 * SWEEP_STAGE_BYTES;
+    cudaFuncSetAttribute(sweep_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         sweep_smem_bytes);
+    sweep_persistent_kernel<<<148, SWEEP_WARPS * 32, sweep_smem_bytes, stream>>>(
+        *m, *ep, *ct, c4, reinterpret_cast<const int2*>(extents), em, kff, tsum, tcount, nchan,
+        tau_rrl, flux_rrl);
+  } else {
+    integrate_continuum_kernel<2><<<(unsigned)ctas, 256, 0, stream>>>(*m, *ep, *ct, c4, em, kff,
+                                                                     tsum, tcount);
+    if (lines)
+      fill_missed_rays_kernel<<<148 * 8, 256, 0, stream>>>(
+          reinterpret_cast<const int2*>(extents), (size_t)nxs * m->nz, nchan, tau_rrl,
+          flux_rrl);
+  }
   if (lines) {
-    // memory-bound work (dense sweep, missed rays) on `stream`, the channel loop beside it
-    fill_missed_rays_kernel<<<148 * 8, 256, 0, stream>>>(
-        reinterpret_cast<const int2*>(extents), (size_t)nxs * m->nz, nchan, tau_rrl, flux_rrl);
     // channel blocks of at most 8 * 256 channels per launch
     for (int c0 = 0; c0 < nchan && n_active > 0; c0 += GCH * LINE_THREADS) {
       const int nc = (nchan - c0 < GCH * LINE_THREADS) ? nchan - c0 : GCH * LINE_THREADS;
