@@ -70,7 +70,7 @@ class ClockSampler:
             self.f = open(self.path, "wt")
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -184,6 +184,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's banner off stdout
         dist.init_process_group("nccl", device_id=dev)
 
     params, cont, line, chans = workload(args.grid, args.nchan)
@@ -277,7 +278,7 @@ def run_gpu(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(f"integrate_line_kernel@{args.grid}x{args.nchan}")
+                traffic = json.load(f).get(f"pass@{args.grid}x{args.nchan}")
         line_out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -290,14 +291,18 @@ def run_gpu(args):
                             "flux_rrl(contsub=False) returned as numpy arrays; inputs are "
                             "the parameter dict (no bulk H2D exists on this path)",
                     "checksum_jy": checksum},
-            "roofline": {"bound": "hbm", "kernel": "integrate_line_kernel (fused K3+K4+K5)",
+            "roofline": {"bound": "hbm",
+                         "kernel": "integration pass: sweep_persistent_kernel (K3, TMA-staged) "
+                                   "|| integrate_line_kernel (K4+K5), two streams",
                          "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": float(kms),
                          "algorithmic_bytes": alg_bytes,
-                         "note": "16 B/cell state + tau and flux cubes + 4 sky images; the "
-                                 "kernel is fp64-pipe bound by the Voigt evaluations of "
-                                 "the in-jet cells, see DESIGN.md"},
+                         "note": "algorithmic bytes = 16 B/cell state + tau and flux cubes + 4 "
+                                 "sky images; the pass is bound by the fp64 pipe (Voigt "
+                                 "evaluations of the in-jet cells in K4, ~75 % pipe-active), "
+                                 "the dense sweep alone runs at the HBM copy bandwidth; "
+                                 "see DESIGN.md section 4 and profiles/README.md"},
         }
         if world == 1 and not args.no_cpu_baseline:
             dt, u = oracle_step(128, 16, 8)
@@ -315,7 +320,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=1024)

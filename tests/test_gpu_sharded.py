@@ -1,0 +1,67 @@
+"""Sharded (x-slab) runs on >= 2 GPUs reproduce the single-GPU products bit for bit
+(each ray is integrated by exactly one rank with the same arithmetic; the exchange is a
+pure all-gather).  Skipped on boxes with one GPU; the gather logic itself is covered on
+CPU by tests/test_sharding_gloo.py."""
+import os
+import socket
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    import scipy.constants as con
+    import torch
+    import torch.distributed as dist
+    import rajepy_b200 as rb
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    log = rb.logger.Log(os.path.join(tempfile.mkdtemp(), f"m{rank}.log"), verbose=False)
+    p = cases.with_grid(cases.base_params(), 64, 96, 128)
+    nu0 = rb.hostmath.rrl_nu_0('H', 58, 1)
+    chans = cases.line_channels(nu0, 96, 2e5)
+    freqs = np.array([5e9, 4.3e10])
+    res = {}
+    for tag, shard in (("one", (0, 1)), ("sharded", (rank, world))):
+        jm = rb.JetModel(p if tag == "one" else cases.with_grid(cases.base_params(), 64, 96, 128),
+                         log=log, device=f"cuda:{rank}", shard=shard)
+        jm.time = 0.9 * con.year
+        res[tag] = (jm.n_verts_inside(), jm.emission_measure(), jm.flux_ff(freqs),
+                    jm.optical_depth_rrl('H58a', chans),
+                    jm.flux_rrl('H58a', chans, contsub=False),
+                    jm.flux_rrl('H58a', chans[:8], contsub=True), jm.temperature)
+    ok = all(np.array_equal(np.nan_to_num(a), np.nan_to_num(b)) and
+             np.array_equal(np.isnan(a), np.isnan(b))
+             for a, b in zip(res["one"], res["sharded"]))
+    open(os.path.join(out_dir, f"r{rank}.txt"), "w").write("ok" if ok else "MISMATCH")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_equals_single_gpu():
+    import torch
+    import torch.multiprocessing as mp
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    tmp = tempfile.mkdtemp()
+    mp.spawn(_worker, args=(world, _free_port(), tmp), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(tmp, f"r{r}.txt")).read() == "ok"
