@@ -1,0 +1,119 @@
+"""BASELINE.json configurations on the GPU.
+
+configs[1] (256^3, 16 continuum frequencies) and configs[3] (burst time series) are checked
+against the oracle directly (at sizes it finishes in a minute or two); configs[2] (512^3 x
+256 channels) and configs[4] (1024^3 x 512 channels) are far beyond the oracle's reach
+(45 / 350 GB of numpy temporaries), so they are checked through size-independent properties:
+mirror symmetry of the sky images, the contsub identity S(contsub=False) - S(contsub=True)
+= S_ff, independence of the result from how the channels are batched, from empty padding
+along the line of sight and from the x-slab decomposition."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import scipy.constants as con
+
+from tests import cases
+from tests.parity import assert_parity, cancellation_floor_ff
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(params, **kw):
+    import rajepy_b200 as rb
+    log = rb.logger.Log(os.path.join(tempfile.mkdtemp(), "m.log"), verbose=False)
+    return rb.JetModel(params, log=log, **kw)
+
+
+def _same(a, b):
+    return np.array_equal(np.isnan(a), np.isnan(b)) and \
+        np.array_equal(np.nan_to_num(a), np.nan_to_num(b))
+
+
+def test_config2_256cube_16_frequencies():
+    """configs[1]: 256^3, continuum at 16 frequencies 1-300 GHz, against the oracle."""
+    from oracle import rajepy_oracle as orc
+    p = cases.with_grid(cases.base_params(), 256, 256, 256)
+    freqs = np.logspace(9, np.log10(3e11), 16)
+    jm, oj = _model(p), orc.OracleJet(cases.with_grid(cases.base_params(), 256, 256, 256))
+    assert np.array_equal(jm.n_verts_inside(), oj.n_verts_inside().astype(np.uint8))
+    assert_parity(jm.emission_measure(), oj.emission_measure(), "EM")
+    assert_parity(jm.optical_depth_ff(freqs), oj.optical_depth_ff(freqs), "tau_ff")
+    assert_parity(jm.flux_ff(freqs), oj.flux_ff(freqs), "S_ff",
+                  floor=cancellation_floor_ff(oj, freqs))
+
+
+def test_config4_burst_time_series():
+    """configs[3]: 4 bursts over epochs 0..5 yr (a subset of the 64), 5 GHz, 96^3."""
+    from oracle import rajepy_oracle as orc
+    p = cases.with_grid(cases.base_params(), 96, 96, 96)
+    jm, oj = _model(p), orc.OracleJet(cases.with_grid(cases.base_params(), 96, 96, 96))
+    totals = []
+    for yr in np.linspace(0., 5., 64)[::9]:
+        jm.time = oj.time = yr * con.year
+        s, so = jm.flux_ff(5e9), oj.flux_ff(5e9)
+        assert_parity(s, so, f"S_ff t={yr:.2f}", floor=cancellation_floor_ff(oj, 5e9)[0])
+        assert_parity(jm.emission_measure(), oj.emission_measure(), f"EM t={yr:.2f}")
+        totals.append(np.nansum(s))
+    assert max(totals) > 1.05 * totals[0]      # the bursts do brighten the jet
+
+
+@pytest.mark.parametrize("n,nch", [(512, 256), (1024, 512)])
+def test_large_grid_properties(n, nch):
+    """configs[2] (512^3, 256 channels) and configs[4] (1024^3, 512 channels)."""
+    import rajepy_b200 as rb
+    p = cases.with_grid(cases.base_params(), n, n, n)
+    jm = _model(p)
+    jm.time = 1.0 * con.year
+    nu0 = rb.hostmath.rrl_nu_0('H', 58, 1)
+    chans = nu0 + (np.arange(nch) - (nch - 1) / 2.) * 1e5
+    em = jm.emission_measure()
+    # (1) the edge-on jet is mirror symmetric in x (bursts only break the z symmetry)
+    assert np.array_equal(em, em[::-1])
+    assert np.count_nonzero(em) > 0.02 * em.size
+    # (2) contsub identity, NaN pattern == rays that miss the jet
+    s_all = jm.flux_rrl('H58a', chans, contsub=False)
+    assert np.array_equal(np.isnan(s_all[0]), em == 0)
+    sub = slice(nch // 2 - 4, nch // 2 + 4)
+    s_cs = jm.flux_rrl('H58a', chans[sub], contsub=True)
+    s_ff = jm.flux_ff(chans[sub])
+    ok = ~np.isnan(s_ff)
+    # both terms are prefactor * (1 - exp(-tau)) formed literally like the reference does:
+    # for optically thin edge pixels that carries an absolute noise of ~ulp(1) * prefactor
+    omega = np.arctan(0.5 * con.au / (120. * con.parsec)) ** 2. / 1e-26
+    pref = (2. * chans[sub] ** 2. * con.k * 1e4 / con.c ** 2. * omega)[:, None, None]
+    lim = 1e-13 * (np.abs(s_cs) + s_ff) + 32 * np.finfo(float).eps * pref
+    assert np.all(np.abs(s_all[sub] - (s_cs + s_ff))[ok] <= lim[ok])
+    # (3) how the channels are batched does not matter (only the summation order of the
+    # cells along a ray may change with the block size: a few ulp)
+    tau = jm.optical_depth_rrl('H58a', chans)
+    half = jm.optical_depth_rrl('H58a', chans[:nch // 2])
+    np.testing.assert_allclose(tau[:nch // 2], half, rtol=1e-13, atol=0)
+    one = jm.optical_depth_rrl('H58a', float(chans[7]))
+    np.testing.assert_allclose(tau[7], one, rtol=1e-13, atol=0)
+    assert tau.min() >= 0.0 and np.array_equal(tau[0] > 0, em > 0)
+    del s_all, s_cs, tau, half
+    jm.release()
+
+
+def test_padding_and_slab_invariance():
+    """Empty cells appended along the line of sight, or cutting the grid into x-slabs,
+    must not change a single bit of the sky images."""
+    import torch
+    p = cases.with_grid(cases.base_params(), 128, 128, 192)
+    jm = _model(p)
+    jm.time = 0.8 * con.year
+    em, tau = jm.emission_measure(), jm.optical_depth_ff(5e9)
+    jp = _model(cases.with_grid(cases.base_params(), 128, 160, 192))
+    jp.time = jm.time
+    assert np.array_equal(jp.emission_measure(), em)
+    assert np.array_equal(jp.optical_depth_ff(5e9), tau)
+    rows = []
+    for r in range(4):
+        js = _model(cases.with_grid(cases.base_params(), 128, 128, 192), shard=(r, 4))
+        js.time = jm.time
+        c = js._pass()                       # slab-local device images, no gather
+        lo, hi = js.slab
+        rows.append(c["em"].view(hi - lo, js.nz).cpu().numpy())
+    assert np.array_equal(np.concatenate(rows, axis=0), em)
