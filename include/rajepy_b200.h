@@ -208,6 +208,14 @@ int rjp_continuum_images(const double* kff, const double* tsum, const int32_t* t
                          double omega_jy, int32_t nfreq, double* tau, double* intensity,
                          double* flux, void* stream);
 
+/* Voigt profile function of the channel loop, element-wise: out[i] = Re w(x[i] + i y[i]),
+ * w = Faddeeva function, y > 0, evaluated by the same device routines the line-of-sight pass
+ * uses (mixed fp64/fp32 split for RJP_VT_Y_MIN <= y <= 0.1, fp64 rational approximation
+ * otherwise).  Replaces scipy.special.wofz at maths/rrls.py:353; exported so that the
+ * parity tests can check the approximation itself against wofz on the device.
+ * x, y, out: DEVICE arrays of n doubles. */
+int rjp_voigt_profile(const double* x, const double* y, int64_t n, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

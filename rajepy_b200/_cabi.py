@@ -62,7 +62,7 @@ _lib = None
 
 EXPORTS = ("rjp_strerror", "rjp_last_cuda_error", "rjp_abi_version", "rjp_struct_sizes",
            "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field", "rjp_ray_list", "rjp_integrate",
-           "rjp_continuum_images")
+           "rjp_continuum_images", "rjp_voigt_profile")
 
 
 def library_path():
@@ -103,9 +103,9 @@ def load():
                                   vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(Line),
                                   C.POINTER(Channels), i32, i32, vp, vp, vp, vp]
     lib.rjp_continuum_images.argtypes = [vp, vp, vp, i64, vp, vp, dbl, i32, vp, vp, vp, vp]
+    lib.rjp_voigt_profile.argtypes = [vp, vp, i64, vp, vp]
     for f in ("rjp_struct_sizes", "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field",
-              "rjp_ray_list",
-              "rjp_integrate", "rjp_continuum_images"):
+              "rjp_ray_list", "rjp_integrate", "rjp_continuum_images", "rjp_voigt_profile"):
         getattr(lib, f).restype = C.c_int
     sizes = [i32() for _ in range(6)]
     lib.rjp_struct_sizes(*[C.byref(s) for s in sizes])

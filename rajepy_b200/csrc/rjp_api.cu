@@ -20,6 +20,7 @@ int rjp_launch_ray_list(const int32_t*, int, int32_t*, int32_t*, cudaStream_t);
 int rjp_launch_continuum_images(const double*, const double*, const int32_t*, int64_t,
                                 const double*, const double*, double, int, double*, double*,
                                 double*, cudaStream_t);
+int rjp_launch_voigt_profile(const double*, const double*, int64_t, double*, cudaStream_t);
 }
 
 static thread_local char g_cuda_err[256] = "";
@@ -137,4 +138,10 @@ extern "C" int rjp_continuum_images(const double* kff, const double* tsum,
   return check_launch(rjp_launch_continuum_images(kff, tsum, tcount, npix, cff, iff, omega_jy,
                                                   nfreq, tau, intensity, flux,
                                                   (cudaStream_t)stream));
+}
+
+extern "C" int rjp_voigt_profile(const double* x, const double* y, int64_t n, double* out,
+                                 void* stream) {
+  if (n < 0 || (n > 0 && (!x || !y || !out))) return RJP_ERR_ARG;
+  return check_launch(rjp_launch_voigt_profile(x, y, n, out, (cudaStream_t)stream));
 }

@@ -357,4 +357,153 @@ __device__ __forceinline__ void faddeeva_wing_n(const double* x, const double* y
   }
 }
 
+
+// ---------------------------------------------------------------- mixed-precision Voigt
+// Cells with a small Lorentz/Gauss ratio, RJP_VT_Y_MIN <= y <= RJP_VT_Y_MAX (97 % of the in-jet
+// cells of the BASELINE jets), take the split K = Re w = 2^(Y^2 - X^2) cos(2xy) - H(x, y)
+// derived in tools/gen_voigt_tables.py: the ill-conditioned Gaussian in fp64, the smooth
+// part H (proportional to y) in fp32, products accumulated in fp64.  Measured against
+// scipy.special.wofz (tests/test_faddeeva.py, same arithmetic emulated in numpy): <= 2.2e-7
+// relative per evaluation, 5e-8 rms, against the 1e-6 bar on the line-of-sight sums.
+// The fp64 <-> fp32 moves are exponent re-biases on the integer pipe: F2F conversions run
+// at 16/clk/SM on B200 (profiles/r1_microbench_mix.txt), a quarter of the DFMA rate.
+#include "rjp_voigt_tables.inc"
+__device__ const float g_vt_core[RJP_VT_NI * RJP_VT_ROW] = {RJP_VT_CORE};
+constexpr int VT_TAB_F4 = RJP_VT_NI * RJP_VT_ROW / 4;
+// constant-bank operands of the DFMAs (no register / uniform-register moves)
+__constant__ double c_vt_exp2[9] = {RJP_VT_EXP2};
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {  // 32-bit shared-window address
+  float4 v;
+  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+struct FastEntry {     // one in-jet cell of the fast class, X = kappa x (80 bytes)
+  double xs;           // X at nu = nu0
+  double inv;          // dX / dnu = kappa / (sigma sqrt2)
+  double yy;           // Y^2 = (kappa y)^2
+  double w0;           // wing lead factor: amp p0 y kappa^2 G1(0)
+  double a0;           // core lead factor: amp p0
+  float c1, c2, c3, c4;  // y-dependent coefficients of the wing polynomial P(U)
+  float yf, y2f;       // y, y^2
+  float ya;            // 2 y / kappa: cos argument per unit X
+  float b1, b2;        // (1 - exp(-h nu / kT)) / p0 = 1 + dn (b1 + dn b2)
+  int xc2_hi;          // high word of the X^2 below which the Gaussian matters
+};
+static_assert(sizeof(FastEntry) == 80, "FastEntry layout");
+
+// (double)v of a positive normal float / its truncating inverse, without F2F
+__device__ __forceinline__ double f2d_pos(float v) {
+  const unsigned b = __float_as_uint(v);
+  return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+}
+__device__ __forceinline__ float d2f_trunc_pos(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v) - 0x38000000u;
+  return __uint_as_float(__funnelshift_l((unsigned)__double2loint(v), hi, 3));
+}
+__device__ __forceinline__ double rcp_seed(double d) {  // MUFU.RCP64H, >= 20 bits
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  return r;
+}
+
+// y-dependent constants of a fast-class cell (once per cell, phase 1 of the channel loop)
+__device__ inline void vt_cell_constants(double y, FastEntry& e) {
+  const double K = RJP_VT_KAPPA;
+  constexpr float g1[] = {RJP_VT_G1}, g3[] = {RJP_VT_G3}, g5[] = {RJP_VT_G5};
+  e.yy = (K * y) * (K * y);
+  const float yyf = (float)e.yy;
+  e.c1 = fmaf(yyf, g3[0], g1[1]);
+  e.c2 = fmaf(yyf, fmaf(yyf, g5[0], g3[1]), g1[2]);
+  e.c3 = fmaf(yyf, fmaf(yyf, g5[1], g3[2]), g1[3]);
+  e.c4 = fmaf(yyf, g3[3], g1[4]);
+  e.yf = (float)y;
+  e.y2f = (float)(y * y);
+  e.ya = (float)(2.0 * y / K);
+  // the Gaussian is dropped where exp(-x^2) < 1e-8 K ~ 1e-8 y / (sqrt(pi) x^2), but never
+  // below the validity limit of the wing polynomials nor beyond the core table
+  const double lc = log(1e8 * 1.7724538509055159 / y);
+  double x2 = lc + log(28.0);
+  x2 = lc + log(x2);
+  x2 = lc + log(x2);
+  e.xc2_hi = __double2hiint(fmin(fmax(x2 * K * K, RJP_VT_XWING2), RJP_VT_XCORE2 - 0.01));
+}
+
+// wings: K = y kappa^2 G1(0) U P(U), U = 1 / X^2; this is P (fp32), U stays in fp64
+__device__ __forceinline__ float vt_wing_poly(const FastEntry& e, float u) {
+  constexpr float g1[] = {RJP_VT_G1};
+  float p = fmaf(g1[6], u, g1[5]);
+  p = fmaf(p, u, e.c4);
+  p = fmaf(p, u, e.c3);
+  p = fmaf(p, u, e.c2);
+  p = fmaf(p, u, e.c1);
+  return fmaf(p, u, 1.0f);
+}
+
+// core: K (fp32) for X^2 < 64; `tab` = shared-window address of g_vt_core staged in
+// shared memory
+__device__ __forceinline__ float vt_core(const FastEntry& e, uint32_t tab, double X,
+                                         double X2) {
+  // |X| 2^25 as an integer from the low mantissa word of |X| + 1.5 2^27
+  const int q = __double2loint(fabs(X) + 201326592.0);
+  const uint32_t row = tab + (uint32_t)(q >> 24) * (RJP_VT_ROW * 4);
+  const float t = fmaf(__int2float_rn(q & 0xFFFFFF), 1.1920928955078125e-07f, -1.0f);
+  const float4 r0 = lds_f4(row), r1 = lds_f4(row + 16), r2 = lds_f4(row + 32),
+               r3 = lds_f4(row + 48), r4 = lds_f4(row + 64);
+  float a = fmaf(r1.w, t, r1.z);
+  a = fmaf(a, t, r1.y);
+  a = fmaf(a, t, r1.x);
+  a = fmaf(a, t, r0.w);
+  a = fmaf(a, t, r0.z);
+  a = fmaf(a, t, r0.y);
+  a = fmaf(a, t, r0.x);
+  float b = fmaf(r3.y, t, r3.x);
+  b = fmaf(b, t, r2.w);
+  b = fmaf(b, t, r2.z);
+  b = fmaf(b, t, r2.y);
+  b = fmaf(b, t, r2.x);
+  float c = fmaf(r4.y, t, r4.x);
+  c = fmaf(c, t, r3.w);
+  c = fmaf(c, t, r3.z);
+  const float hy = fmaf(e.y2f, fmaf(e.y2f, c, b), a);          // H / y
+  // Gaussian 2^(Y^2 - X^2) in fp64: round-to-integer by the 1.5 2^52 shift, degree-8
+  // polynomial of 2^f on [-1/2, 1/2] (pre-scaled by 1 + 2^-25: the truncation below rounds)
+  const double T = e.yy - X2;
+  const double M = T + 6755399441055744.0;
+  const double f = T - (M - 6755399441055744.0);
+  double p = fma(c_vt_exp2[8], f, c_vt_exp2[7]);
+#pragma unroll
+  for (int k = 6; k >= 0; --k) p = fma(p, f, c_vt_exp2[k]);
+  const unsigned hi = (unsigned)__double2hiint(p) + ((unsigned)__double2loint(M) << 20) -
+                      0x38000000u;
+  const float g = __uint_as_float(__funnelshift_l((unsigned)__double2loint(p), hi, 3));
+  // cos(2xy) - 1, 2xy = X * ya <= 1.4
+  const float w = (__int2float_rn(q) * 2.98023223876953125e-08f) * e.ya;
+  const float w2 = w * w;
+  float cs = fmaf(-2.755731922398589e-07f, w2, 2.48015873015873e-05f);
+  cs = fmaf(cs, w2, -1.388888888888889e-03f);
+  cs = fmaf(cs, w2, 4.1666666666666664e-02f);
+  cs = fmaf(cs, w2, -0.5f);
+  return fmaf(-e.yf, hy, fmaf(g, w2 * cs, g));
+}
+
+// Re w(x + iy) with the routines of the channel loop (diagnostic entry rjp_voigt_profile)
+__device__ inline double voigt_any(uint32_t tab, double x, double y) {
+  if (y >= RJP_VT_Y_MIN && y <= RJP_VT_Y_MAX) {
+    FastEntry e;
+    vt_cell_constants(y, e);
+    const double X = RJP_VT_KAPPA * x, X2 = X * X;
+    if (__double2hiint(X2) < e.xc2_hi) return f2d_pos(vt_core(e, tab, X, X2));
+    const double r0 = rcp_seed(X2), U = r0 * fma(-X2, r0, 2.0);
+    return (y * RJP_VT_KAPPA * RJP_VT_KAPPA * RJP_VT_G10) * U *
+           f2d_pos(vt_wing_poly(e, d2f_trunc_pos(r0)));
+  }
+  double xv[1] = {x}, yv[1] = {y}, w[1];
+  if (x * x + y * y >= 36.0) faddeeva_wing_n<1>(xv, yv, w);
+  else faddeeva_re_n<1>(xv, yv, w);
+  return w[0];
+}
+
 }  // namespace rjp

@@ -1,25 +1,28 @@
 // Line-of-sight integration for sm_100a: K3 (continuum sums), K4 (LTE recombination-
 // line opacity over all velocity channels) and K5 (image / cube epilogue).
 //
-// K3 `integrate_continuum_kernel` -- the dense sweep: every 16-byte cell of the slab is
-// read from HBM exactly once.  A CTA owns 32 adjacent rays (fixed x, 32 consecutive z)
-// over the whole line of sight; lanes run along z so every warp-wide load is one
-// contiguous 512-byte row, warps stride along y with RPW rows in flight each.  Sums
-// are fp64 registers per (warp, ray), reduced across the CTA's warps through shared
-// memory -- no atomics, deterministic order.  HBM-bound.
+// The grid fill records, per ray, the y-extent [y_lo, y_hi) of its in-jet cells and the list
+// of rays that cross the jet at all (0.4 % of the cells, 6 % of the rays of the BASELINE
+// 1024^3 grid).  The pass walks exactly those extents and never touches the empty part of
+// the 16 B/cell state:
 //
-// K4 `integrate_line_kernel` -- the channel loop: fp64-pipe bound, so it is shaped for
-// the math, not for streaming.  The fill recorded, per ray, the y-extent [y_lo, y_hi) of
-// its in-jet cells and the list of rays that cross the jet at all.  One CTA owns ONE such
-// ray; thread g owns channels 8g..8g+7 and keeps their tau_L in REGISTERS while the CTA
-// walks the ray's extent: the threads each prepare one cell (burst factor, Doppler shift,
-// widths, amplitude -> shared-memory entry), then every thread adds all prepared cells
-// to its channels.  All lanes of a warp work on the same cell list (no divergence), rays
-// of different length never wait for each other, and the hardware scheduler balances
-// the ~5 % of rays that carry all the work.  Rays that miss the jet get 0 / NaN from a
-// plain streaming kernel.  K4 re-reads only the in-jet cells (< 1 % of the grid).  The
-// memory-bound kernels (K3, missed rays) and K4 are independent and are launched on two
-// streams so that the HBM-bound work overlaps the compute-bound channel loop.
+// K4 `integrate_line_kernel` -- the channel loop, one CTA per jet-crossing ray: thread g
+// owns channels g, g + NT, ... and keeps their tau_L in REGISTERS while the CTA walks the
+// ray's extent: the threads each prepare one cell (burst factor, Doppler shift, widths,
+// amplitude -> shared-memory entry), then every thread adds all prepared cells to its
+// channels.  The Voigt function is the mixed fp64/fp32 split of rjp_device.cuh for cells
+// with y <= 0.1 and the fp64 rational approximation otherwise.  Issue-bound.  The same
+// walk yields the ray's continuum sums (EM, K, sum T, count) and the flux epilogue.
+//
+// K3 `continuum_rays_kernel` -- continuum-only passes: one warp per jet-crossing ray.
+// `missed_rays_kernel` streams the constants (0 / NaN) of the rays that miss the jet into
+// the images and cubes -- the only HBM-bound part of the pass (write-only), run beside
+// the channel loop on the caller's first stream.
+//
+// `integrate_continuum_kernel` -- the dense sweep for callers that have a cell state but no
+// extents: every 16-byte cell read once, CTA = 32 adjacent rays, lanes along z so every
+// warp-wide load is one contiguous 512-byte row, 8 rows in flight per warp; measured at the
+// HBM copy bandwidth (profiles/README.md).
 #include "rjp_device.cuh"
 
 namespace rjp {
@@ -263,26 +266,93 @@ __device__ __noinline__ LineEntry make_entry(const Decoded& d, const rjp_model& 
   return e;
 }
 
+// Fast class (rjp_device.cuh, "mixed-precision Voigt"): small Lorentz/Gauss ratio and a
+// Planck factor that is a short polynomial in the channel offset.
+__device__ __forceinline__ bool fast_class(const LineEntry& e) {
+  return e.amp != 0.0 && e.hk < 0.0 && e.y >= RJP_VT_Y_MIN && e.y <= RJP_VT_Y_MAX;
+}
+
+__device__ __noinline__ FastEntry to_fast(const LineEntry& s) {
+  FastEntry e;
+  vt_cell_constants(s.y, e);
+  e.xs = RJP_VT_KAPPA * s.xs;
+  e.inv = RJP_VT_KAPPA * s.inv_s2;
+  e.a0 = s.amp * s.p0;
+  e.w0 = e.a0 * s.y * (RJP_VT_KAPPA * RJP_VT_KAPPA * RJP_VT_G10);
+  e.b1 = (float)(s.a1 / s.p0);
+  e.b2 = (float)(s.a2 / s.p0);
+  return e;
+}
+
 // 1 - exp(-h nu / kT) for nu = nu0 + dn from the cell's value at nu0 (rrls.py:387)
 __device__ __forceinline__ double planck_factor(const LineEntry& e, double dn) {
   if (e.hk < 0.0) return fma(dn, fma(dn, fma(dn, e.a3, e.a2), e.a1), e.p0);
   return e.p0 + (1.0 - e.p0) * (-expm1(-e.hk * dn));
 }
 
-// Rays that miss the jet: tau_L = 0, flux = NaN in every channel (nansum / nanmean of an
-// all-NaN column).  Pure streaming writes; rays that cross the jet are
-// left to the channel loop, so the two kernels can run concurrently in any order.
-__global__ void fill_missed_rays_kernel(const int2* __restrict__ extents, size_t nray,
-                                        int nchan, double* __restrict__ tau,
-                                        double* __restrict__ flux) {
-  const size_t n = nray * (size_t)nchan;
+// Rays that miss the jet: EM = K = sum T = 0, count = 0, tau_L = 0 and flux = NaN in every
+// channel (nansum / nanmean of an all-NaN column).  Pure streaming writes;
+// rays that cross the jet are left to the ray kernels, so the two can run concurrently.
+__global__ void missed_rays_kernel(const int2* __restrict__ extents, size_t nray, int nchan,
+                                   double* __restrict__ em, double* __restrict__ kff,
+                                   double* __restrict__ tsum, int32_t* __restrict__ tcount,
+                                   double* __restrict__ tau, double* __restrict__ flux) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const double nanv = dnan();
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (size_t i = t0; i < nray; i += stride) {
+    const int2 e = __ldg(extents + i);
+    if (e.x < e.y) continue;
+    em[i] = 0.0;
+    kff[i] = 0.0;
+    tsum[i] = 0.0;
+    tcount[i] = 0;
+  }
+  const size_t n = nray * (size_t)nchan;
+  for (size_t i = t0; i < n; i += stride) {
     const int2 e = __ldg(extents + (i % nray));
     if (e.x < e.y) continue;
     if (tau) tau[i] = 0.0;
     if (flux) flux[i] = nanv;
+  }
+}
+
+// Continuum-only walk: one warp per jet-crossing ray, lanes stride along the extent.
+__global__ void __launch_bounds__(256)
+continuum_rays_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
+                      const double2* __restrict__ cells, const int2* __restrict__ extents,
+                      const int32_t* __restrict__ ray_list, const int n_active,
+                      double* __restrict__ em, double* __restrict__ kff,
+                      double* __restrict__ tsum, int32_t* __restrict__ tcount) {
+  __shared__ Params s_p;
+  stage_params(&s_p, m, ep);
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n_active) return;
+  const int ray = ray_list[w];
+  const int xl = ray / m.nz, iz = ray - xl * m.nz;
+  const int ix = m.x_lo + xl;
+  const int2 ext = extents[ray];
+  const Ray rc = ray_of(s_p.m, ix, iz);
+  const double2* col = cells + (size_t)xl * m.ny * m.nz + iz;
+  ContAcc a = {0.0, 0.0, 0.0, 0};
+  for (int iy = ext.x + lane; iy < ext.y; iy += 32) {
+    const double2 c = col[(size_t)iy * m.nz];
+    if (empty_cell(c)) continue;
+    accumulate(a, decode(c, s_p, rc, ix, iy, iz), ct.t_exponent);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a.em += __shfl_xor_sync(0xffffffffu, a.em, o);
+    a.kff += __shfl_xor_sync(0xffffffffu, a.kff, o);
+    a.tsum += __shfl_xor_sync(0xffffffffu, a.tsum, o);
+    a.cnt += __shfl_xor_sync(0xffffffffu, a.cnt, o);
+  }
+  if (lane == 0) {
+    em[ray] = a.em * ct.em_scale;
+    kff[ray] = a.kff * ct.tau_scale;
+    tsum[ray] = a.tsum;
+    tcount[ray] = a.cnt;
   }
 }
 
@@ -310,17 +380,27 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
                       const rjp_line ln, const rjp_channels ch, const int nchan,
                       const int contsub, const double dn_max,
                       const double2* __restrict__ cells, const int2* __restrict__ extents,
-                      const int32_t* __restrict__ ray_list, double* __restrict__ tau_rrl,
+                      const int32_t* __restrict__ ray_list, double* __restrict__ em,
+                      double* __restrict__ kff, double* __restrict__ tsum,
+                      int32_t* __restrict__ tcount, double* __restrict__ tau_rrl,
                       double* __restrict__ flux_rrl) {
   __shared__ Params s_p;
   __shared__ rjp_line s_ln;
-  __shared__ LineEntry s_list[LINE_THREADS + 4];
-  __shared__ double s_part[2][LINE_THREADS];
-  __shared__ int s_pcnt[LINE_THREADS];
-  __shared__ int s_woff[LINE_THREADS / 32 + 1];
+  // one batch of prepared cells: fast-class entries from the front, the others behind them
+  // (both are 80 bytes; +3 zero-amplitude pads for the 4-cell batches of the fp64 path)
+  __shared__ __align__(16) unsigned char s_raw[(MAXT + 4) * sizeof(LineEntry)];
+  __shared__ float4 s_tab[VT_TAB_F4];
+  __shared__ double s_part[3][MAXT];
+  __shared__ int s_pcnt[MAXT];
+  __shared__ int s_woff[2][MAXT / 32 + 1];
+  static_assert(sizeof(LineEntry) == sizeof(FastEntry), "shared batch buffer");
   stage_params(&s_p, m, ep);
   if (threadIdx.x == 0) s_ln = ln;
+  for (int i = threadIdx.x; i < VT_TAB_F4; i += blockDim.x)
+    s_tab[i] = reinterpret_cast<const float4*>(g_vt_core)[i];
 
+  uint32_t tab = (uint32_t)__cvta_generic_to_shared(s_tab);
+  asm volatile("" : "+r"(tab));  // keep it in a register (rematerialising costs S2R + LEA)
   const int NT = blockDim.x;
   const int g = threadIdx.x, lane = g & 31, wrp = g >> 5, nwarps = NT >> 5;
   const int ray = ray_list[blockIdx.x];          // slab-local ray index = xl * nz + iz
@@ -331,11 +411,14 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
 
   // thread g owns channels g, g + NT, g + 2 NT, ...: at every step the lanes of a warp hold
   // 32 neighbouring channels, i.e. nearly the same point of the line profile, so the
-  // core / wing branch below is warp-uniform
+  // core / wing branches below are (almost always) warp-uniform
   double dn[GCH];
+  float dnf[GCH];
 #pragma unroll
-  for (int j = 0; j < GCH; ++j)
+  for (int j = 0; j < GCH; ++j) {
     dn[j] = (g + j * NT < nchan) ? __ldg(ch.dnu + g + j * NT) : 0.0;
+    dnf[j] = (float)dn[j];
+  }
   double acc[GCH];
 #pragma unroll
   for (int j = 0; j < GCH; ++j) acc[j] = 0.0;
@@ -345,8 +428,8 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   __syncthreads();
 
   for (int y0 = ext.x; y0 < ext.y; y0 += NT) {
-    // phase 1: every thread prepares one cell of the extent; cells that emit no line
-    // are dropped by an ordered compaction (deterministic summation order)
+    // phase 1: every thread prepares one cell of the extent; cells that emit no line are
+    // dropped and the two classes are compacted in order (deterministic summation order)
     const int iy = y0 + g;
     LineEntry e;
     e.amp = 0.0;
@@ -358,47 +441,84 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
         if (d.ne_ok && d.t_ok) e = make_entry(d, s_p.m, s_ln, dn_max, ix, iy, iz);
       }
     }
-    const bool keep = e.amp != 0.0;
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) s_woff[wrp] = __popc(bal);
-    __syncthreads();
-    int base = 0, n = 0;
-    for (int w = 0; w < nwarps; ++w) {
-      if (w < wrp) base += s_woff[w];
-      n += s_woff[w];
+    const bool fast = fast_class(e);
+    const bool slow = e.amp != 0.0 && !fast;
+    const unsigned balf = __ballot_sync(0xffffffffu, fast);
+    const unsigned bals = __ballot_sync(0xffffffffu, slow);
+    if (lane == 0) {
+      s_woff[0][wrp] = __popc(balf);
+      s_woff[1][wrp] = __popc(bals);
     }
-    if (keep) s_list[base + __popc(bal & ((1u << lane) - 1u))] = e;
     __syncthreads();
-    if (g < 3 && n > 0) {  // pad the last batch of 4 with zero-amplitude copies
-      LineEntry pad = s_list[n - 1];
+    int basef = 0, bases = 0, nf = 0, ns = 0;
+    for (int w = 0; w < nwarps; ++w) {
+      if (w < wrp) {
+        basef += s_woff[0][w];
+        bases += s_woff[1][w];
+      }
+      nf += s_woff[0][w];
+      ns += s_woff[1][w];
+    }
+    FastEntry* s_fast = reinterpret_cast<FastEntry*>(s_raw);
+    LineEntry* s_slow = reinterpret_cast<LineEntry*>(s_raw) + nf;
+    const unsigned below = (1u << lane) - 1u;
+    if (fast) s_fast[basef + __popc(balf & below)] = to_fast(e);
+    if (slow) s_slow[bases + __popc(bals & below)] = e;
+    __syncthreads();
+    if (g < 3 && ns > 0) {  // pad the last batch of 4 with zero-amplitude copies
+      LineEntry pad = s_slow[ns - 1];
       pad.amp = 0.0;
-      s_list[n + g] = pad;
+      s_slow[ns + g] = pad;
     }
     __syncthreads();
 
-    // phase 2: every thread adds all prepared cells to its channels, 4 cells at a time
-    // (channel loop outermost: the running sum and the channel offset stay in registers)
-#pragma unroll 1
-    for (int j = 0; j < GCH; ++j) {
-      if (g + j * NT >= nchan) break;
-      const double dnj = dn[j];
-      double sum = 0.0;
-      for (int i = 0; i < n; i += 4) {
-        const LineEntry* eb = s_list + i;
-        double x[4], yy[4], w[4];
-        bool wing = true;
+    // phase 2a, fast class: every thread adds each prepared cell to its GCH channels.  The
+    // wing term is evaluated branch-free for all channels (8 independent chains per
+    // thread); channels inside the Gaussian core replace it by the table evaluation.
+    for (int i = 0; i < nf; ++i) {
+      const FastEntry fe = s_fast[i];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          x[v] = fma(dnj, eb[v].inv_s2, eb[v].xs);
-          yy[v] = eb[v].y;
-          wing = wing && (fma(x[v], x[v], yy[v] * yy[v]) >= 36.0);
+      for (int j = 0; j < GCH; ++j) {
+        const double X = fma(dn[j], fe.inv, fe.xs);
+        const double X2 = X * X;
+        const double r0 = rcp_seed(X2);
+        double lead = fe.w0 * (r0 * fma(-X2, r0, 2.0));
+        float kf = vt_wing_poly(fe, d2f_trunc_pos(r0));
+        if (__double2hiint(X2) < fe.xc2_hi) {
+          kf = vt_core(fe, tab, X, X2);
+          lead = fe.a0;
         }
-        if (wing) faddeeva_wing_n<4>(x, yy, w);
-        else faddeeva_re_n<4>(x, yy, w);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) sum = fma(eb[v].amp * w[v], planck_factor(eb[v], dnj), sum);
+        const float eps = dnf[j] * fmaf(dnf[j], fe.b2, fe.b1);
+        acc[j] = fma(lead, f2d_pos(fmaf(kf, eps, kf)), acc[j]);
       }
-      acc[j] += sum;
+    }
+
+    // phase 2b, everything else in fp64 (large or tiny y, steep Planck factor): 4 cells at a
+    // time, channel loop outermost
+    if (ns > 0) {
+#pragma unroll 1
+      for (int j = 0; j < GCH; ++j) {
+        if (g + j * NT >= nchan) break;
+        const double dnj = dn[j];
+        double sum = 0.0;
+        for (int i = 0; i < ns; i += 4) {
+          const LineEntry* eb = s_slow + i;
+          double x[4], yy[4], w[4];
+          bool wing = true;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            x[v] = fma(dnj, eb[v].inv_s2, eb[v].xs);
+            yy[v] = eb[v].y;
+            wing = wing && (fma(x[v], x[v], yy[v] * yy[v]) >= 36.0);
+          }
+          if (wing) faddeeva_wing_n<4>(x, yy, w);
+          else faddeeva_re_n<4>(x, yy, w);
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            sum = fma(eb[v].amp * w[v], planck_factor(eb[v], dnj), sum);
+        }
+        acc[j] += sum;
+      }
     }
     __syncthreads();
   }
@@ -406,16 +526,24 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   // the ray's continuum sums (needed by the flux epilogue): reduce the NT partials
   s_part[0][g] = ca.kff;
   s_part[1][g] = ca.tsum;
+  s_part[2][g] = ca.em;
   s_pcnt[g] = ca.cnt;
   __syncthreads();
-  double kray = 0.0, ts = 0.0;
+  double kray = 0.0, ts = 0.0, emr = 0.0;
   int cn = 0;
   for (int i = 0; i < NT; ++i) {
     kray += s_part[0][i];
     ts += s_part[1][i];
+    emr += s_part[2][i];
     cn += s_pcnt[i];
   }
   kray *= ct.tau_scale;
+  if (g == 0 && em != nullptr) {  // first channel block only: the ray's continuum images
+    em[ray] = emr * ct.em_scale;
+    kff[ray] = kray;
+    tsum[ray] = ts;
+    tcount[ray] = cn;
+  }
 
   // K5 epilogue: rrls.py:444-447, physics.py:571-574, classes.py:1323-1328, :1484-1488
   const double tmean = ts / (double)cn;
@@ -438,136 +566,16 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   }
 }
 
-// ------------------------------------------------------------------ sweep beside the loop
-// Persistent, bulk-copy-staged form of the dense sweep for passes that also run the channel
-// loop.  A small grid (one 4-warp CTA per SM) is resident from the start and leaves most
-// of every SM to the compute-bound loop, so the two overlap instead of queueing behind
-// each other (the block scheduler drains one kernel's CTAs before the other's).  With
-// only four warps per SM the loads cannot live in registers: each warp streams its tile
-// (32 rays x all y) through a two-stage shared-memory ring filled by the TMA engine with
-// 1-D bulk copies (cp.async.bulk, one 512-byte z-row per copy, SWEEP_ROWS rows per stage,
-// completion on an mbarrier), i.e. 16 KB in flight per warp at no register cost.  Same
-// arithmetic as integrate_continuum_kernel, no cross-warp reduction; the warp also
-// writes 0 / NaN into the cubes for the rays of its tile that miss the jet.
-constexpr int SWEEP_ROWS = 16;
-constexpr int SWEEP_WARPS = 4;
-constexpr int SWEEP_STAGE_BYTES = SWEEP_ROWS * ZT * 16;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        " selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
-                                         uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-__global__ void __launch_bounds__(SWEEP_WARPS * 32, 1)
-sweep_persistent_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
-                        const double2* __restrict__ cells, const int2* __restrict__ extents,
-                        double* __restrict__ em, double* __restrict__ kff,
-                        double* __restrict__ tsum, int32_t* __restrict__ tcount,
-                        const int nchan, double* __restrict__ tau_rrl,
-                        double* __restrict__ flux_rrl) {
-  extern __shared__ __align__(128) unsigned char sweep_smem[];
-  __shared__ Params s_p;
-  __shared__ __align__(8) unsigned long long s_bar[SWEEP_WARPS][2];
-  stage_params(&s_p, m, ep);
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  unsigned char* ring = sweep_smem + (size_t)wrp * 2 * SWEEP_STAGE_BYTES;
-  const uint32_t bar0 = smem_u32(&s_bar[wrp][0]), bar1 = smem_u32(&s_bar[wrp][1]);
-  if (lane == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar1, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-
-  const int ztiles = (m.nz + ZT - 1) / ZT;
-  const long long ntiles = (long long)(m.x_hi - m.x_lo) * ztiles;
-  const size_t plane = (size_t)(m.x_hi - m.x_lo) * m.nz;
-  const int nchunks = (m.ny + SWEEP_ROWS - 1) / SWEEP_ROWS;
-  uint32_t ph0 = 0, ph1 = 0;  // phase parity of the two stage barriers
-
-  for (long long tile = (long long)blockIdx.x * SWEEP_WARPS + wrp; tile < ntiles;
-       tile += (long long)gridDim.x * SWEEP_WARPS) {
-    const int xl = (int)(tile / ztiles);
-    const int z0 = (int)(tile % ztiles) * ZT;
-    const int iz = z0 + lane;
-    const int nlanes = min(ZT, m.nz - z0);          // rays of this tile
-    const bool active = lane < nlanes;
-    const uint32_t row_bytes = (uint32_t)nlanes * 16u;
-    const double2* base = cells + (size_t)xl * m.ny * m.nz + z0;
-    const int ix = m.x_lo + xl;
-    const Ray ray = ray_of(s_p.m, ix, active ? iz : z0);
-    ContAcc a = {0.0, 0.0, 0.0, 0};
-
-    // producer: lane 0 asks the TMA engine for the rows of chunk c into stage c & 1
-    auto issue = [&](int c) {
-      const int y0 = c * SWEEP_ROWS;
-      const int rows = min(SWEEP_ROWS, m.ny - y0);
-      const uint32_t bar = (c & 1) ? bar1 : bar0;
-      const uint32_t dst = smem_u32(ring + (size_t)(c & 1) * SWEEP_STAGE_BYTES);
-      mbar_expect_tx(bar, (uint32_t)rows * row_bytes);
-      for (int r = 0; r < rows; ++r)
-        bulk_g2s(dst + (uint32_t)r * (ZT * 16), base + (size_t)(y0 + r) * m.nz, row_bytes, bar);
-    };
-    if (lane == 0) {
-      issue(0);
-      if (nchunks > 1) issue(1);
-    }
-    for (int c = 0; c < nchunks; ++c) {
-      const int st = c & 1;
-      if (st) { mbar_wait(bar1, ph1); ph1 ^= 1; } else { mbar_wait(bar0, ph0); ph0 ^= 1; }
-      const int y0 = c * SWEEP_ROWS;
-      const int rows = min(SWEEP_ROWS, m.ny - y0);
-      const double2* rowp = reinterpret_cast<const double2*>(ring + (size_t)st * SWEEP_STAGE_BYTES);
-      if (active) {
-        for (int r = 0; r < rows; ++r) {
-          const double2 cell = rowp[r * ZT + lane];
-          if (empty_cell(cell)) continue;
-          accumulate(a, decode(cell, s_p, ray, ix, y0 + r, iz), ct.t_exponent);
-        }
-      }
-      __syncwarp();
-      if (lane == 0 && c + 2 < nchunks) {
-        // the stage was read through the generic proxy: order that before the async writes
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(c + 2);
-      }
-    }
-    if (!active) continue;
-    const size_t pix = (size_t)xl * m.nz + iz;
-    em[pix] = a.em * ct.em_scale;
-    kff[pix] = a.kff * ct.tau_scale;
-    tsum[pix] = a.tsum;
-    tcount[pix] = a.cnt;
-    const int2 e = extents[pix];
-    if (e.x >= e.y) {  // the channel loop never visits this ray
-      const double nanv = dnan();
-      for (int c = 0; c < nchan; ++c) {
-        if (tau_rrl) tau_rrl[(size_t)c * plane + pix] = 0.0;
-        if (flux_rrl) flux_rrl[(size_t)c * plane + pix] = nanv;
-      }
-    }
-  }
+// Diagnostic: Re w(x + iy) with the channel loop's own device routines
+__global__ void voigt_profile_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                     int64_t n, double* __restrict__ out) {
+  __shared__ float4 s_tab[VT_TAB_F4];
+  for (int i = threadIdx.x; i < VT_TAB_F4; i += blockDim.x)
+    s_tab[i] = reinterpret_cast<const float4*>(g_vt_core)[i];
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = voigt_any((uint32_t)__cvta_generic_to_shared(s_tab), x[i], y[i]);
 }
 
 // ------------------------------------------------------------------ continuum images
@@ -621,11 +629,21 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
   const long long ctas = (long long)nxs * ((m->nz + ZT - 1) / ZT);
   if (ctas <= 0 || ctas > 2147483647LL) return RJP_ERR_ARG;
   const double2* c4 = reinterpret_cast<const double2*>(cells);
+  const int2* ex2 = reinterpret_cast<const int2*>(extents);
   const bool lines = nchan > 0 && ln != nullptr;
+  if (extents == nullptr || (n_active > 0 && ray_list == nullptr)) {
+    // no extents: dense sweep over the whole state (continuum only; the API demands extents
+    // for line passes)
+    if (lines) return RJP_ERR_ARG;
+    integrate_continuum_kernel<2><<<(unsigned)ctas, 256, 0, stream>>>(*m, *ep, *ct, c4, em, kff,
+                                                                     tsum, tcount);
+    return RJP_OK;
+  }
+  const size_t nray = (size_t)nxs * m->nz;
   cudaEvent_t fork = nullptr, join = nullptr;
   cudaStream_t ls = stream;
-  if (lines && stream2 != nullptr && stream2 != stream) {
-    // fork: the channel loop runs beside the dense sweep
+  if (lines && n_active > 0 && stream2 != nullptr && stream2 != stream) {
+    // fork: the issue-bound channel loop runs beside the write-bound constant fill
     if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess)
       return RJP_ERR_CUDA;
@@ -633,54 +651,54 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
     cudaStreamWaitEvent(stream2, fork, 0);
     ls = stream2;
   }
-  if (lines && fork && n_active > 0) {
-    // memory-bound work (dense sweep + missed rays) as a small persistent grid on `stream`,
-    // resident beside the channel loop on `stream2`
-    const int sweep_smem_bytes = SWEEP_WARPS * 2 * SWEEP_STAGE_BYTES;
-    cudaFuncSetAttribute(sweep_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         sweep_smem_bytes);
-    sweep_persistent_kernel<<<148, SWEEP_WARPS * 32, sweep_smem_bytes, stream>>>(
-        *m, *ep, *ct, c4, reinterpret_cast<const int2*>(extents), em, kff, tsum, tcount, nchan,
-        tau_rrl, flux_rrl);
-  } else {
-    integrate_continuum_kernel<2><<<(unsigned)ctas, 256, 0, stream>>>(*m, *ep, *ct, c4, em, kff,
-                                                                     tsum, tcount);
-    if (lines)
-      fill_missed_rays_kernel<<<148 * 8, 256, 0, stream>>>(
-          reinterpret_cast<const int2*>(extents), (size_t)nxs * m->nz, nchan, tau_rrl,
-          flux_rrl);
-  }
-  if (lines) {
-    // channel blocks of at most 8 * 256 channels per launch
-    for (int c0 = 0; c0 < nchan && n_active > 0; c0 += GCH * LINE_THREADS) {
+  if (lines && n_active > 0) {
+    // channel blocks of at most 8 * 256 channels per launch; the first one also writes the
+    // continuum images of its rays
+    for (int c0 = 0; c0 < nchan; c0 += GCH * LINE_THREADS) {
       const int nc = (nchan - c0 < GCH * LINE_THREADS) ? nchan - c0 : GCH * LINE_THREADS;
       const int groups = (nc + GCH - 1) / GCH;
       const int threads = ((groups + 31) / 32) * 32;
       rjp_channels cb = *ch;
       cb.dnu += c0; cb.nu += c0; cb.cff += c0; cb.aff += c0; cb.bnu += c0;
-      const size_t off = (size_t)c0 * nxs * m->nz;
-      const int2* ex2 = reinterpret_cast<const int2*>(extents);
+      const size_t off = (size_t)c0 * nray;
       double* t_out = tau_rrl ? tau_rrl + off : nullptr;
       double* f_out = flux_rrl ? flux_rrl + off : nullptr;
-      // 128 registers per thread at every block size (measured best on B200: 8 CTAs of 64
-      // threads per SM; see profiles/README.md)
+      double* em_o = (c0 == 0) ? em : nullptr;
+      // 128 registers per thread at every block size (8 CTAs of 64 threads per SM)
       if (threads <= 64)
         integrate_line_kernel<64, 8><<<(unsigned)n_active, threads, 0, ls>>>(
-            *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, t_out, f_out);
+            *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, em_o, kff, tsum, tcount,
+            t_out, f_out);
       else if (threads <= 128)
         integrate_line_kernel<128, 4><<<(unsigned)n_active, threads, 0, ls>>>(
-            *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, t_out, f_out);
+            *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, em_o, kff, tsum, tcount,
+            t_out, f_out);
       else
         integrate_line_kernel<LINE_THREADS, 2><<<(unsigned)n_active, threads, 0, ls>>>(
-            *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, t_out, f_out);
+            *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, em_o, kff, tsum, tcount,
+            t_out, f_out);
     }
+  } else if (n_active > 0) {
+    continuum_rays_kernel<<<(n_active + 7) / 8, 256, 0, stream>>>(*m, *ep, *ct, c4, ex2, ray_list,
+                                                                 n_active, em, kff, tsum, tcount);
   }
+  missed_rays_kernel<<<148 * 8, 256, 0, stream>>>(ex2, nray, lines ? nchan : 0, em, kff, tsum,
+                                                  tcount, tau_rrl, flux_rrl);
   if (fork) {
     cudaEventRecord(join, stream2);
     cudaStreamWaitEvent(stream, join, 0);
     cudaEventDestroy(fork);
     cudaEventDestroy(join);
   }
+  return RJP_OK;
+}
+
+extern "C" int rjp_launch_voigt_profile(const double* x, const double* y, int64_t n,
+                                        double* out, cudaStream_t stream) {
+  if (n <= 0) return RJP_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  voigt_profile_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, y, n, out);
   return RJP_OK;
 }
 

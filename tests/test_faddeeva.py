@@ -68,3 +68,36 @@ def test_voigt_far_wings_stay_relative():
         ref = wofz(xs + 1j * y).real
         rel = np.abs(faddeeva_re(xs, y) - ref) / ref
         assert rel.max() < 1e-6, (y, rel)
+
+
+# ---------------------------------------------------------------- mixed-precision split
+def test_fast_tables_generator_is_reproducible():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "gen_voigt_tables", os.path.join(ROOT, "tools", "gen_voigt_tables.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    committed = open(os.path.join(ROOT, "rajepy_b200", "csrc", "rjp_voigt_tables.inc")).read()
+    assert mod.render() == committed
+
+
+def test_fast_voigt_emulation_against_wofz():
+    """The fp64/fp32 split of the channel loop, emulated operation by operation in numpy
+    (tests/voigt_emul.py), against scipy.special.wofz over the whole fast class."""
+    from tests import voigt_emul as ve
+    t = ve.load_tables()
+    xs = np.linspace(-60.0, 60.0, 48001)
+    for y in (1e-9, 1e-7, 1e-5, 1e-3, 4.5e-3, 0.011, 0.03, 0.06, 0.1):
+        ref = wofz(xs + 1j * y).real
+        rel = np.abs(ve.voigt_fast(xs, y, t) / ref - 1.0)
+        assert rel.max() < 3e-7, (y, rel.max(), xs[rel.argmax()])
+        assert np.sqrt(np.mean(rel ** 2)) < 8e-8, y
+
+
+def test_fast_voigt_far_wings():
+    from tests import voigt_emul as ve
+    t = ve.load_tables()
+    xs = np.array([80.0, 300.0, 1e3, 1e4, 1e6])
+    for y in (1e-6, 1e-2, 0.1):
+        ref = wofz(xs + 1j * y).real
+        assert np.abs(ve.voigt_fast(xs, y, t) / ref - 1.0).max() < 2e-7
