@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RJP_ABI_VERSION 1
+#define RJP_ABI_VERSION 2
 #define RJP_MAX_BURSTS 16
 
 enum {
@@ -142,17 +142,28 @@ int rjp_struct_sizes(int32_t* model, int32_t* epoch, int32_t* continuum, int32_t
  *                          then re-run with a larger list)
  *   extents [slab rays][2] int32: per ray (x, z) the half-open y-range [y_lo, y_hi)
  *                          that contains all of its in-jet cells (y_lo >= y_hi: the ray
- *                          misses the jet); written here, read by the channel loop    */
+ *                          misses the jet); written here, read by the ray kernels
+ *   brick_state [rjp_brick_count()] uint8, optional (NULL: every cell is written):
+ *                          occupancy map of the caller's nverts / cells buffers in bricks of
+ *                          4 x 8 x 32 cells.  0 = this brick of both buffers is all zero,
+ *                          non-zero = it holds data.  The fill skips bricks that lie outside
+ *                          the jet and are already zero, zeroes bricks that lie outside but
+ *                          hold data, and updates the map -- so on a zero-initialised or
+ *                          recycled buffer it writes only the bricks around the jet.        */
 int rjp_fill_grid(const rjp_model* m_host, uint8_t* nverts, rjp_cell* cells,
-                  int32_t* ties, int32_t tie_capacity, int32_t* n_ties,
-                  int32_t* extents, void* stream);
+                  uint8_t* brick_state, int32_t* ties, int32_t tie_capacity,
+                  int32_t* n_ties, int32_t* extents, void* stream);
+
+/* Number of bricks (entries of brick_state) of the slab described by m_host; < 0 = error. */
+int64_t rjp_brick_count(const rjp_model* m_host);
 
 /* Apply host-resolved vertex decisions: for n cells (flat slab indices `cell_idx`,
  * device) set nverts to `new_count` (device, uint8), recompute the packed state and
  * widen the ray extents where a cell enters the jet. */
 int rjp_patch_cells(const rjp_model* m_host, const int64_t* cell_idx,
                     const uint8_t* new_count, int32_t n, uint8_t* nverts,
-                    rjp_cell* cells, int32_t* extents, void* stream);
+                    rjp_cell* cells, uint8_t* brick_state /* optional */, int32_t* extents,
+                    void* stream);
 
 /* Full-precision 3-D property planes on demand (float64, NaN outside the jet where the
  * reference has NaN), for the JetModel properties the plotting code reads. */
@@ -187,6 +198,9 @@ int rjp_ray_list(const int32_t* extents, int64_t nray, int32_t* list, int32_t* n
  * the nanmean temperature of intensity_ff (:1471-1473), optical_depth_rrl (:1130-1229)
  * and intensity_rrl/flux_rrl (:1231-1351).
  *   em, kff, tsum [nxs*nz] double, tcount [nxs*nz] int32 (always written)
+ *   extents / ray_list (from rjp_fill_grid / rjp_ray_list): the pass walks only the recorded
+ *   in-jet extents of the listed rays and never reads the empty part of the state; with
+ *   extents = NULL (continuum-only passes) every cell of the state is swept instead.
  *   line/ch may be NULL/nchan = 0 for a continuum-only pass; otherwise
  *   tau_rrl and/or flux_rrl ([nchan][nxs][nz] double) may each be NULL.
  *   contsub: 0 -> flux_rrl includes S_ff (what Pipeline requests, classes.py:2450).

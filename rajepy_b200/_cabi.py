@@ -62,7 +62,7 @@ _lib = None
 
 EXPORTS = ("rjp_strerror", "rjp_last_cuda_error", "rjp_abi_version", "rjp_struct_sizes",
            "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field", "rjp_ray_list", "rjp_integrate",
-           "rjp_continuum_images", "rjp_voigt_profile")
+           "rjp_continuum_images", "rjp_voigt_profile", "rjp_brick_count")
 
 
 def library_path():
@@ -95,8 +95,10 @@ def load():
     lib.rjp_abi_version.restype = C.c_int
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     lib.rjp_struct_sizes.argtypes = [C.POINTER(i32)] * 6
-    lib.rjp_fill_grid.argtypes = [C.POINTER(Model), vp, vp, vp, i32, vp, vp, vp]
-    lib.rjp_patch_cells.argtypes = [C.POINTER(Model), vp, vp, i32, vp, vp, vp, vp]
+    lib.rjp_fill_grid.argtypes = [C.POINTER(Model), vp, vp, vp, vp, i32, vp, vp, vp]
+    lib.rjp_patch_cells.argtypes = [C.POINTER(Model), vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.rjp_brick_count.argtypes = [C.POINTER(Model)]
+    lib.rjp_brick_count.restype = i64
     lib.rjp_cell_field.argtypes = [C.POINTER(Model), C.POINTER(Epoch), vp, i32, vp, vp]
     lib.rjp_ray_list.argtypes = [vp, i64, vp, vp, vp]
     lib.rjp_integrate.argtypes = [C.POINTER(Model), C.POINTER(Epoch), C.POINTER(Continuum),

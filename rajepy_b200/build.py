@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "librajepy_b200.so")
+LIB = os.environ.get("RAJEPY_B200_LIB") or os.path.join(LIBDIR, "librajepy_b200.so")
 SOURCES = ["rjp_api.cu", "rjp_fill.cu", "rjp_integrate.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-std=c++17", "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -39,7 +39,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    extra = os.environ.get("RAJEPY_B200_NVCC_EXTRA", "").split()  # kernel-variant experiments
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(LIBDIR, "build.log"), "wt") as f:

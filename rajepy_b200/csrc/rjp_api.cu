@@ -6,10 +6,11 @@
 #include "../../include/rajepy_b200.h"
 
 extern "C" {
-int rjp_launch_fill(const rjp_model*, uint8_t*, rjp_cell*, int32_t*, int32_t, int32_t*,
-                    int32_t*, cudaStream_t);
+int rjp_launch_fill(const rjp_model*, uint8_t*, rjp_cell*, uint8_t*, int32_t*, int32_t,
+                    int32_t*, int32_t*, cudaStream_t);
+long long rjp_launch_brick_count(const rjp_model*);
 int rjp_launch_patch(const rjp_model*, const int64_t*, const uint8_t*, int32_t, uint8_t*,
-                     rjp_cell*, int32_t*, cudaStream_t);
+                     rjp_cell*, uint8_t*, int32_t*, cudaStream_t);
 int rjp_launch_field(const rjp_model*, const rjp_epoch*, const uint8_t*, int32_t, double*,
                      cudaStream_t);
 int rjp_launch_integrate(const rjp_model*, const rjp_epoch*, const rjp_continuum*,
@@ -67,24 +68,30 @@ extern "C" int rjp_struct_sizes(int32_t* model, int32_t* epoch, int32_t* continu
   return RJP_OK;
 }
 
+extern "C" int64_t rjp_brick_count(const rjp_model* m) {
+  if (!model_ok(m)) return RJP_ERR_ARG;
+  return (int64_t)rjp_launch_brick_count(m);
+}
+
 extern "C" int rjp_fill_grid(const rjp_model* m, uint8_t* nverts, rjp_cell* cells,
-                             int32_t* ties, int32_t tie_capacity, int32_t* n_ties,
-                             int32_t* extents, void* stream) {
+                             uint8_t* brick_state, int32_t* ties, int32_t tie_capacity,
+                             int32_t* n_ties, int32_t* extents, void* stream) {
   if (!model_ok(m) || !nverts || !cells || !n_ties || !extents || tie_capacity < 0 ||
       (tie_capacity > 0 && !ties))
     return RJP_ERR_ARG;
-  return check_launch(rjp_launch_fill(m, nverts, cells, ties, tie_capacity, n_ties, extents,
-                                      (cudaStream_t)stream));
+  return check_launch(rjp_launch_fill(m, nverts, cells, brick_state, ties, tie_capacity, n_ties,
+                                      extents, (cudaStream_t)stream));
 }
 
 extern "C" int rjp_patch_cells(const rjp_model* m, const int64_t* cell_idx,
                                const uint8_t* new_count, int32_t n, uint8_t* nverts,
-                               rjp_cell* cells, int32_t* extents, void* stream) {
+                               rjp_cell* cells, uint8_t* brick_state, int32_t* extents,
+                               void* stream) {
   if (!model_ok(m) || n < 0 || (n > 0 && (!cell_idx || !new_count)) || !nverts || !cells ||
       !extents)
     return RJP_ERR_ARG;
-  return check_launch(rjp_launch_patch(m, cell_idx, new_count, n, nverts, cells, extents,
-                                       (cudaStream_t)stream));
+  return check_launch(rjp_launch_patch(m, cell_idx, new_count, n, nverts, cells, brick_state,
+                                       extents, (cudaStream_t)stream));
 }
 
 extern "C" int rjp_cell_field(const rjp_model* m, const rjp_epoch* ep, const uint8_t* nverts,

@@ -1,125 +1,147 @@
 // Grid fill for sm_100a: K1 (8-vertex inside test, classes.py:657-669) fused with K2
 // (per-cell state, classes.py:838-1095).
 //
-// One CTA owns a TX x TY x TZ brick of cells.  The (TX+1)(TY+1)(TZ+1) lattice vertices
-// of the brick are tested ONCE each (instead of 8 times, as the reference's eight grid
-// passes do) and their inside bits are staged in shared memory; every cell then sums
-// its eight corner bits.  Lanes run along z, the contiguous axis, so the 16-byte
-// state stores and the 1-byte count stores of a warp are fully coalesced (512 B / 32 B).
-// No input is read from HBM: the pass is bounded by the 17 B/cell it writes and by
-// the fp64 pipe (vertex transform + sqrt); `pow` runs only for vertices that an fp32
-// estimate cannot decide and for cells inside the jet.
+// The grid is cut into bricks of TX x TY x TZ cells.  A brick that provably lies outside
+// the jet (conservative bound on its circumscribed sphere) is all zeros; every other brick
+// tests its (TX+1)(TY+1)(TZ+1) lattice vertices ONCE each (instead of 8 times, as the
+// reference's eight grid passes do), stages the inside bits in shared memory, and every cell
+// sums its eight corner bits.  Lanes run along z, the contiguous axis, so the 16-byte state
+// stores and the 1-byte count stores of a warp are fully coalesced (512 B / 32 B).  No input
+// is read from HBM.  One CTA owns a super-brick of SBX x SBY bricks (32^3 cells): its first
+// warp decides all 32 bricks at once, then the CTA walks the bricks that need work.
+//
+// `brick_state` (optional, one byte per brick) makes the fill sparse: it records which bricks
+// of the caller's nverts / cells buffers hold data.  A rejected brick whose state is 0 is
+// already zero and is not written at all, so with a zero-initialised (or previously used)
+// buffer the fill writes only the ~3 % of bricks around the jet instead of 17 B for every
+// cell of the grid.  Without it every brick is written (dense behaviour).
 #include "rjp_device.cuh"
 
 namespace rjp {
 
 constexpr int TX = 4, TY = 8, TZ = 32;
+constexpr int SBX = 8, SBY = 4;            // bricks per super-brick along x and y
 constexpr int FILL_THREADS = 256;
 constexpr int NVERT = (TX + 1) * (TY + 1) * (TZ + 1);
 
+// Conservative whole-brick rejection (the jet fills < 1-15 % of the grid).  Every vertex v of
+// the brick lies within R_b of the brick centre c, so w_v >= w_c - R_b and
+// |r_v| <= |r_c| + R_b; the jet width w_0 rho(|r|)^eps grows with |r| (eps > 0), hence no
+// vertex can pass the inside test if w_c - R_b > w_jet(|r_c| + R_b) (or if the whole brick is
+// below the launch radius).  The 1e-6 margin dwarfs rounding, so the integer counts are
+// unchanged: such bricks are all zeros.
+__device__ inline bool brick_outside(const rjp_model& m, int tx0, int ty0, int tz0) {
+  if (!(m.eps > 0.0 && m.w0 > 0.0)) return false;
+  const double hx = 0.5 * TX * m.cs, hy = 0.5 * TY * m.cs, hz = 0.5 * TZ * m.cs;
+  const Rw c = xyz_to_rw(m, corner(m.cs, tx0, m.nx) + hx, corner(m.cs, ty0, m.ny) + hy,
+                         corner(m.cs, tz0, m.nz) + hz);
+  const double rb = sqrt(hx * hx + hy * hy + hz * hz) * (1.0 + 1e-9);
+  const double rmax = fabs(c.r) + rb;
+  if (rmax < m.r0 * (1.0 - 1e-9)) return true;
+  const double rh = rho_of(m, rmax);
+  return rh > 0.0 && (c.w - rb) > m.w0 * pow(rh, m.eps) * (1.0 + 1e-6);
+}
+
 __global__ void __launch_bounds__(FILL_THREADS)
 fill_grid_kernel(const rjp_model m, uint8_t* __restrict__ nverts,
-                 rjp_cell* __restrict__ cells, int32_t* __restrict__ ties,
-                 int32_t tie_capacity, int32_t* __restrict__ n_ties,
-                 int32_t* __restrict__ extents) {
+                 rjp_cell* __restrict__ cells, uint8_t* __restrict__ brick_state,
+                 int32_t* __restrict__ ties, int32_t tie_capacity,
+                 int32_t* __restrict__ n_ties, int32_t* __restrict__ extents) {
   __shared__ uint8_t s_in[NVERT];
-  const int tiles_z = (m.nz + TZ - 1) / TZ;
+  __shared__ int s_todo[SBX * SBY];   // 0 nothing, 1 write zeros, 2 compute
+  const int nxs = m.x_hi - m.x_lo;
+  const int tiles_x = (nxs + TX - 1) / TX;
   const int tiles_y = (m.ny + TY - 1) / TY;
+  const int tiles_z = (m.nz + TZ - 1) / TZ;
+  const int sup_y = (tiles_y + SBY - 1) / SBY;
   int t = blockIdx.x;
-  const int tz0 = (t % tiles_z) * TZ; t /= tiles_z;
-  const int ty0 = (t % tiles_y) * TY; t /= tiles_y;
-  const int tx0 = m.x_lo + t * TX;
+  const int bz = t % tiles_z; t /= tiles_z;
+  const int sy = t % sup_y;
+  const int sx = t / sup_y;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
 
-  // Conservative whole-brick rejection (the jet fills < 1-15 % of the grid).  Every vertex
-  // v of the brick lies within R_b of the brick centre c, so w_v >= w_c - R_b and
-  // |r_v| <= |r_c| + R_b; the jet width w_0 rho(|r|)^eps grows with |r| (eps > 0), hence
-  // no vertex can pass the inside test if w_c - R_b > w_jet(|r_c| + R_b) (or if the whole
-  // brick is below the launch radius).  The 1e-6 margin dwarfs rounding, so the integer
-  // counts are unchanged: such bricks are all zeros and are written without any test.
-  // (decided by one thread, broadcast through shared memory: the bound needs a pow)
-  __shared__ int s_skip;
-  if (threadIdx.x == 0) {
-    bool skip0 = false;
-    if (m.eps > 0.0 && m.w0 > 0.0) {
-      const double hx = 0.5 * TX * m.cs, hy = 0.5 * TY * m.cs, hz = 0.5 * TZ * m.cs;
-      const Rw c = xyz_to_rw(m, corner(m.cs, tx0, m.nx) + hx, corner(m.cs, ty0, m.ny) + hy,
-                             corner(m.cs, tz0, m.nz) + hz);
-      const double rb = sqrt(hx * hx + hy * hy + hz * hz) * (1.0 + 1e-9);
-      const double rmax = fabs(c.r) + rb;
-      if (rmax < m.r0 * (1.0 - 1e-9)) {
-        skip0 = true;
-      } else {
-        const double rh = rho_of(m, rmax);
-        if (rh > 0.0) skip0 = (c.w - rb) > m.w0 * pow(rh, m.eps) * (1.0 + 1e-6);
-      }
+  if (threadIdx.x < SBX * SBY) {
+    const int bx = sx * SBX + threadIdx.x / SBY, by = sy * SBY + threadIdx.x % SBY;
+    int todo = 0;
+    if (bx < tiles_x && by < tiles_y) {
+      const bool out = brick_outside(m, m.x_lo + bx * TX, by * TY, bz * TZ);
+      const size_t bid = ((size_t)bx * tiles_y + by) * tiles_z + bz;
+      const bool holds_data = brick_state ? brick_state[bid] != 0 : true;
+      todo = out ? (holds_data ? 1 : 0) : 2;
+      if (brick_state) brick_state[bid] = out ? 0 : 1;
     }
-    s_skip = skip0 ? 1 : 0;
+    s_todo[threadIdx.x] = todo;
   }
   __syncthreads();
-  const bool skip = s_skip != 0;
-  if (skip) {
-    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-#pragma unroll
-    for (int lx = 0; lx < TX; ++lx) {
-      const int ix = tx0 + lx, iy = ty0 + wrp, iz = tz0 + lane;
-      if (ix >= m.x_hi || iy >= m.ny || iz >= m.nz) continue;
-      const size_t idx = ((size_t)(ix - m.x_lo) * m.ny + iy) * m.nz + iz;
-      nverts[idx] = 0;
-      reinterpret_cast<double2*>(cells)[idx] = make_double2(0.0, 0.0);
-    }
-    return;
-  }
 
-  for (int v = threadIdx.x; v < NVERT; v += FILL_THREADS) {
-    const int lz = v % (TZ + 1);
-    const int ly = (v / (TZ + 1)) % (TY + 1);
-    const int lx = v / ((TZ + 1) * (TY + 1));
-    const int I = tx0 + lx, J = ty0 + ly, K = tz0 + lz;
-    int res = 0;
-    if (I <= m.x_hi && J <= m.ny && K <= m.nz) {
-      res = vertex_inside(m, corner(m.cs, I, m.nx), corner(m.cs, J, m.ny),
-                          corner(m.cs, K, m.nz));
-      // report each near-tie once: by the brick that owns the vertex (lower faces),
-      // or by the last brick at the slab / grid upper faces
-      const bool own = (lx < TX || I == m.x_hi) && (ly < TY || J == m.ny) &&
-                       (lz < TZ || K == m.nz);
-      if ((res & 2) && own) {
-        const int slot = atomicAdd(n_ties, 1);
-        if (slot < tie_capacity) {
-          ties[4 * slot + 0] = I;
-          ties[4 * slot + 1] = J;
-          ties[4 * slot + 2] = K;
-          ties[4 * slot + 3] = res & 1;
+  for (int k = 0; k < SBX * SBY; ++k) {
+    const int todo = s_todo[k];            // uniform over the CTA
+    if (todo == 0) continue;
+    const int tx0 = m.x_lo + (sx * SBX + k / SBY) * TX;
+    const int ty0 = (sy * SBY + k % SBY) * TY;
+    const int tz0 = bz * TZ;
+    if (todo == 1) {
+#pragma unroll
+      for (int lx = 0; lx < TX; ++lx) {
+        const int ix = tx0 + lx, iy = ty0 + wrp, iz = tz0 + lane;
+        if (ix >= m.x_hi || iy >= m.ny || iz >= m.nz) continue;
+        const size_t idx = ((size_t)(ix - m.x_lo) * m.ny + iy) * m.nz + iz;
+        nverts[idx] = 0;
+        reinterpret_cast<double2*>(cells)[idx] = make_double2(0.0, 0.0);
+      }
+      continue;
+    }
+
+    for (int v = threadIdx.x; v < NVERT; v += FILL_THREADS) {
+      const int lz = v % (TZ + 1);
+      const int ly = (v / (TZ + 1)) % (TY + 1);
+      const int lx = v / ((TZ + 1) * (TY + 1));
+      const int I = tx0 + lx, J = ty0 + ly, K = tz0 + lz;
+      int res = 0;
+      if (I <= m.x_hi && J <= m.ny && K <= m.nz) {
+        res = vertex_inside(m, corner(m.cs, I, m.nx), corner(m.cs, J, m.ny),
+                            corner(m.cs, K, m.nz));
+        // report each near-tie once: by the brick that owns the vertex (lower faces),
+        // or by the last brick at the slab / grid upper faces
+        const bool own = (lx < TX || I == m.x_hi) && (ly < TY || J == m.ny) &&
+                         (lz < TZ || K == m.nz);
+        if ((res & 2) && own) {
+          const int slot = atomicAdd(n_ties, 1);
+          if (slot < tie_capacity) {
+            ties[4 * slot + 0] = I;
+            ties[4 * slot + 1] = J;
+            ties[4 * slot + 2] = K;
+            ties[4 * slot + 3] = res & 1;
+          }
         }
       }
+      s_in[v] = (uint8_t)(res & 1);
     }
-    s_in[v] = (uint8_t)(res & 1);
-  }
-  __syncthreads();
+    __syncthreads();
 
-  const int lane = threadIdx.x & 31;
-  const int wrp = threadIdx.x >> 5;  // == local y
 #pragma unroll
-  for (int lx = 0; lx < TX; ++lx) {
-    const int ix = tx0 + lx, iy = ty0 + wrp, iz = tz0 + lane;
-    if (ix >= m.x_hi || iy >= m.ny || iz >= m.nz) continue;
-    int cnt = 0;
+    for (int lx = 0; lx < TX; ++lx) {
+      const int ix = tx0 + lx, iy = ty0 + wrp, iz = tz0 + lane;  // warp index == local y
+      if (ix >= m.x_hi || iy >= m.ny || iz >= m.nz) continue;
+      int cnt = 0;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int vx = lx + (c & 1), vy = wrp + ((c >> 1) & 1), vz = lane + (c >> 2);
-      cnt += s_in[(vx * (TY + 1) + vy) * (TZ + 1) + vz];
+      for (int c = 0; c < 8; ++c) {
+        const int vx = lx + (c & 1), vy = wrp + ((c >> 1) & 1), vz = lane + (c >> 2);
+        cnt += s_in[(vx * (TY + 1) + vy) * (TZ + 1) + vz];
+      }
+      const size_t idx = ((size_t)(ix - m.x_lo) * m.ny + iy) * m.nz + iz;
+      nverts[idx] = (uint8_t)cnt;
+      rjp_cell c = {0.0, 0.0};
+      if (cnt > 0) {
+        c = pack_cell(m, ix, iy, iz, cnt);
+        // y-extent of the ray's in-jet cells, for the ray kernels of the integration pass
+        int32_t* e = extents + 2 * ((size_t)(ix - m.x_lo) * m.nz + iz);
+        atomicMin(e, iy);
+        atomicMax(e + 1, iy + 1);
+      }
+      reinterpret_cast<double2*>(cells)[idx] = make_double2(c.ne0, c.temp);
     }
-    const size_t idx = ((size_t)(ix - m.x_lo) * m.ny + iy) * m.nz + iz;
-    nverts[idx] = (uint8_t)cnt;
-    rjp_cell c = {0.0, 0.0};
-    if (cnt > 0) {
-      c = pack_cell(m, ix, iy, iz, cnt);
-      // y-extent of the ray's in-jet cells, for the channel loop (K4)
-      int32_t* e = extents + 2 * ((size_t)(ix - m.x_lo) * m.nz + iz);
-      atomicMin(e, iy);
-      atomicMax(e + 1, iy + 1);
-    }
-    reinterpret_cast<double2*>(cells)[idx] = make_double2(c.ne0, c.temp);
+    __syncthreads();   // s_in is reused by the next brick
   }
 }
 
@@ -132,6 +154,7 @@ __global__ void patch_cells_kernel(const rjp_model m, const int64_t* __restrict_
                                    const uint8_t* __restrict__ new_count, int32_t n,
                                    uint8_t* __restrict__ nverts,
                                    rjp_cell* __restrict__ cells,
+                                   uint8_t* __restrict__ brick_state,
                                    int32_t* __restrict__ extents) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -147,6 +170,10 @@ __global__ void patch_cells_kernel(const rjp_model m, const int64_t* __restrict_
     int32_t* e = extents + 2 * ((size_t)(ix - m.x_lo) * m.nz + iz);
     atomicMin(e, iy);
     atomicMax(e + 1, iy + 1);
+    if (brick_state) {
+      const int tiles_y = (m.ny + TY - 1) / TY, tiles_z = (m.nz + TZ - 1) / TZ;
+      brick_state[((size_t)((ix - m.x_lo) / TX) * tiles_y + iy / TY) * tiles_z + iz / TZ] = 1;
+    }
   }
   cells[idx] = c;
 }
@@ -206,27 +233,34 @@ cell_field_kernel(const rjp_model m, const rjp_epoch ep, const uint8_t* __restri
 
 using namespace rjp;
 
+extern "C" long long rjp_launch_brick_count(const rjp_model* m) {
+  const int nxs = m->x_hi - m->x_lo;
+  return (long long)((nxs + TX - 1) / TX) * ((m->ny + TY - 1) / TY) * ((m->nz + TZ - 1) / TZ);
+}
+
 extern "C" int rjp_launch_fill(const rjp_model* m, uint8_t* nverts, rjp_cell* cells,
-                               int32_t* ties, int32_t tie_capacity, int32_t* n_ties,
-                               int32_t* extents, cudaStream_t stream) {
+                               uint8_t* brick_state, int32_t* ties, int32_t tie_capacity,
+                               int32_t* n_ties, int32_t* extents, cudaStream_t stream) {
   const int nxs = m->x_hi - m->x_lo;
   const size_t nray = (size_t)nxs * m->nz;
   init_extents_kernel<<<(unsigned)((nray + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<int2*>(extents), nray);
-  const long long tiles = (long long)((nxs + TX - 1) / TX) * ((m->ny + TY - 1) / TY) *
-                          ((m->nz + TZ - 1) / TZ);
-  if (tiles <= 0 || tiles > 2147483647LL) return RJP_ERR_ARG;
-  fill_grid_kernel<<<(unsigned)tiles, FILL_THREADS, 0, stream>>>(
-      *m, nverts, cells, ties, tie_capacity, n_ties, extents);
+  const int tiles_x = (nxs + TX - 1) / TX, tiles_y = (m->ny + TY - 1) / TY;
+  const long long sup = (long long)((tiles_x + SBX - 1) / SBX) * ((tiles_y + SBY - 1) / SBY) *
+                        ((m->nz + TZ - 1) / TZ);
+  if (sup <= 0 || sup > 2147483647LL) return RJP_ERR_ARG;
+  fill_grid_kernel<<<(unsigned)sup, FILL_THREADS, 0, stream>>>(
+      *m, nverts, cells, brick_state, ties, tie_capacity, n_ties, extents);
   return RJP_OK;
 }
 
 extern "C" int rjp_launch_patch(const rjp_model* m, const int64_t* cell_idx,
                                 const uint8_t* new_count, int32_t n, uint8_t* nverts,
-                                rjp_cell* cells, int32_t* extents, cudaStream_t stream) {
+                                rjp_cell* cells, uint8_t* brick_state, int32_t* extents,
+                                cudaStream_t stream) {
   if (n <= 0) return RJP_OK;
-  patch_cells_kernel<<<(n + 127) / 128, 128, 0, stream>>>(*m, cell_idx, new_count, n,
-                                                         nverts, cells, extents);
+  patch_cells_kernel<<<(n + 127) / 128, 128, 0, stream>>>(*m, cell_idx, new_count, n, nverts,
+                                                         cells, brick_state, extents);
   return RJP_OK;
 }
 

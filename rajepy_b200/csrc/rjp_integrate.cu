@@ -29,7 +29,16 @@ namespace rjp {
 
 constexpr int ZT = 32;          // rays per CTA of the dense sweep
 constexpr int RPW = 8;          // rows in flight per warp
-constexpr int GCH = 8;          // channels per thread of the line kernel
+#ifndef RJP_VARIANT
+#define RJP_VARIANT 0
+#endif
+#ifndef RJP_GCH
+#define RJP_GCH 8
+#endif
+#ifndef RJP_MINB64
+#define RJP_MINB64 8
+#endif
+constexpr int GCH = RJP_GCH;    // channels per thread of the line kernel
 constexpr int LINE_THREADS = 256;
 
 struct LineEntry {   // channel-independent factors of one in-jet cell (rrls.py:329-389)
@@ -284,6 +293,13 @@ __device__ __noinline__ FastEntry to_fast(const LineEntry& s) {
   return e;
 }
 
+__device__ __noinline__ float vt_core_call(double yy, float y2f, float yf, float ya, uint32_t tab,
+                                           double X, double X2) {
+  FastEntry e;
+  e.yy = yy; e.y2f = y2f; e.yf = yf; e.ya = ya;
+  return vt_core(e, tab, X, X2);
+}
+
 // 1 - exp(-h nu / kT) for nu = nu0 + dn from the cell's value at nu0 (rrls.py:387)
 __device__ __forceinline__ double planck_factor(const LineEntry& e, double dn) {
   if (e.hk < 0.0) return fma(dn, fma(dn, fma(dn, e.a3, e.a2), e.a1), e.p0);
@@ -293,27 +309,48 @@ __device__ __forceinline__ double planck_factor(const LineEntry& e, double dn) {
 // Rays that miss the jet: EM = K = sum T = 0, count = 0, tau_L = 0 and flux = NaN in every
 // channel (nansum / nanmean of an all-NaN column).  Pure streaming writes;
 // rays that cross the jet are left to the ray kernels, so the two can run concurrently.
-__global__ void missed_rays_kernel(const int2* __restrict__ extents, size_t nray, int nchan,
-                                   double* __restrict__ em, double* __restrict__ kff,
-                                   double* __restrict__ tsum, int32_t* __restrict__ tcount,
-                                   double* __restrict__ tau, double* __restrict__ flux) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+missed_rays_kernel(const int2* __restrict__ extents, size_t nray, int nchan,
+                   double* __restrict__ em, double* __restrict__ kff,
+                   double* __restrict__ tsum, int32_t* __restrict__ tcount,
+                   double* __restrict__ tau, double* __restrict__ flux) {
+  // persistent: a warp takes 128 consecutive rays at a time (4 per lane) and loops over the
+  // channel planes -- no loads inside the store stream; one light CTA per SM leaves the rest
+  // of the SM to the channel loop
+  const int lane = threadIdx.x & 31;
+  const size_t gw = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t nw = (size_t)gridDim.x * (blockDim.x >> 5);
   const double nanv = dnan();
-  for (size_t i = t0; i < nray; i += stride) {
-    const int2 e = __ldg(extents + i);
-    if (e.x < e.y) continue;
-    em[i] = 0.0;
-    kff[i] = 0.0;
-    tsum[i] = 0.0;
-    tcount[i] = 0;
-  }
-  const size_t n = nray * (size_t)nchan;
-  for (size_t i = t0; i < n; i += stride) {
-    const int2 e = __ldg(extents + (i % nray));
-    if (e.x < e.y) continue;
-    if (tau) tau[i] = 0.0;
-    if (flux) flux[i] = nanv;
+  for (size_t r0 = gw * 128; r0 < nray; r0 += nw * 128) {
+    bool miss[4];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t ray = r0 + lane + 32 * k;
+      miss[k] = false;
+      if (ray < nray) {
+        const int2 e = __ldg(extents + ray);
+        miss[k] = e.x >= e.y;
+      }
+      if (miss[k]) {
+        em[ray] = 0.0;
+        kff[ray] = 0.0;
+        tsum[ray] = 0.0;
+        tcount[ray] = 0;
+      }
+      any = any || miss[k];
+    }
+    if (!any) continue;
+    for (int c = 0; c < nchan; ++c) {
+      const size_t o = (size_t)c * nray + r0 + lane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (miss[k]) {
+          if (tau) tau[o + 32 * k] = 0.0;
+          if (flux) flux[o + 32 * k] = nanv;
+        }
+      }
+    }
   }
 }
 
@@ -481,6 +518,26 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
       for (int j = 0; j < GCH; ++j) {
         const double X = fma(dn[j], fe.inv, fe.xs);
         const double X2 = X * X;
+#if RJP_VARIANT == 1
+        double lead;
+        float kf;
+        if (__double2hiint(X2) < fe.xc2_hi) {
+          kf = vt_core(fe, tab, X, X2);
+          lead = fe.a0;
+        } else {
+          const double r0 = rcp_seed(X2);
+          lead = fe.w0 * (r0 * fma(-X2, r0, 2.0));
+          kf = vt_wing_poly(fe, d2f_trunc_pos(r0));
+        }
+#elif RJP_VARIANT == 2
+        const double r0 = rcp_seed(X2);
+        double lead = fe.w0 * (r0 * fma(-X2, r0, 2.0));
+        float kf = vt_wing_poly(fe, d2f_trunc_pos(r0));
+        if (__double2hiint(X2) < fe.xc2_hi) {
+          kf = vt_core_call(fe.yy, fe.y2f, fe.yf, fe.ya, tab, X, X2);
+          lead = fe.a0;
+        }
+#else
         const double r0 = rcp_seed(X2);
         double lead = fe.w0 * (r0 * fma(-X2, r0, 2.0));
         float kf = vt_wing_poly(fe, d2f_trunc_pos(r0));
@@ -488,6 +545,7 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
           kf = vt_core(fe, tab, X, X2);
           lead = fe.a0;
         }
+#endif
         const float eps = dnf[j] * fmaf(dnf[j], fe.b2, fe.b1);
         acc[j] = fma(lead, f2d_pos(fmaf(kf, eps, kf)), acc[j]);
       }
@@ -642,8 +700,9 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
   const size_t nray = (size_t)nxs * m->nz;
   cudaEvent_t fork = nullptr, join = nullptr;
   cudaStream_t ls = stream;
-  if (lines && n_active > 0 && stream2 != nullptr && stream2 != stream) {
-    // fork: the issue-bound channel loop runs beside the write-bound constant fill
+  if (n_active > 0 && stream2 != nullptr && stream2 != stream) {
+    // fork (before the constant fill is queued): the issue-bound ray walk on stream2 runs
+    // beside the write-bound constant fill on stream
     if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess)
       return RJP_ERR_CUDA;
@@ -651,6 +710,10 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
     cudaStreamWaitEvent(stream2, fork, 0);
     ls = stream2;
   }
+  // constants of the rays that miss the jet: one light persistent CTA per SM, launched first
+  // so that it is resident beside the ray kernels
+  missed_rays_kernel<<<148, 256, 0, stream>>>(ex2, nray, lines ? nchan : 0, em, kff, tsum, tcount,
+                                              tau_rrl, flux_rrl);
   if (lines && n_active > 0) {
     // channel blocks of at most 8 * 256 channels per launch; the first one also writes the
     // continuum images of its rays
@@ -666,7 +729,7 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
       double* em_o = (c0 == 0) ? em : nullptr;
       // 128 registers per thread at every block size (8 CTAs of 64 threads per SM)
       if (threads <= 64)
-        integrate_line_kernel<64, 8><<<(unsigned)n_active, threads, 0, ls>>>(
+        integrate_line_kernel<64, RJP_MINB64><<<(unsigned)n_active, threads, 0, ls>>>(
             *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, em_o, kff, tsum, tcount,
             t_out, f_out);
       else if (threads <= 128)
@@ -679,11 +742,9 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
             t_out, f_out);
     }
   } else if (n_active > 0) {
-    continuum_rays_kernel<<<(n_active + 7) / 8, 256, 0, stream>>>(*m, *ep, *ct, c4, ex2, ray_list,
+    continuum_rays_kernel<<<(n_active + 7) / 8, 256, 0, ls>>>(*m, *ep, *ct, c4, ex2, ray_list,
                                                                  n_active, em, kff, tsum, tcount);
   }
-  missed_rays_kernel<<<148 * 8, 256, 0, stream>>>(ex2, nray, lines ? nchan : 0, em, kff, tsum,
-                                                  tcount, tau_rrl, flux_rrl);
   if (fork) {
     cudaEventRecord(join, stream2);
     cudaStreamWaitEvent(stream, join, 0);

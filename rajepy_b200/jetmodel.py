@@ -42,6 +42,41 @@ def _torch():
     return torch
 
 
+# Grid-state buffers (vertex counts 1 B/cell + packed cells 16 B/cell) are recycled between
+# models of the same slab size together with their per-brick occupancy map: the fill then
+# rewrites only the bricks around the jet (and zeroes bricks that held data of the previous
+# model) instead of the whole 17 B/cell state.  A buffer that is not in the pool is allocated
+# zero-filled, which is the state an all-zero occupancy map describes.
+_STATE_POOL = {}
+
+
+def _take_state(torch, dev, ncell, nbricks):
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), ncell, nbricks)
+    hit = _STATE_POOL.pop(key, None)
+    if hit is not None:
+        return hit
+    return (torch.zeros(ncell, dtype=torch.uint8, device=dev),
+            torch.zeros((ncell, 2), dtype=torch.float64, device=dev),
+            torch.zeros(max(nbricks, 1), dtype=torch.uint8, device=dev))
+
+
+def _give_state(d):
+    """Return a model's state buffers to the pool (at most one set per slab size)."""
+    try:
+        dev = d["device"]
+        key = (dev.index, d["nverts"].numel(), d["bricks"].numel())
+        if d["bricks"].numel() >= 1:
+            _STATE_POOL.clear()
+            _STATE_POOL[key] = (d["nverts"], d["cells"], d["bricks"])
+    except Exception:  # noqa: BLE001 -- recycling is an optimisation only
+        pass
+
+
+def clear_state_pool():
+    """Free the recycled grid-state buffers."""
+    _STATE_POOL.clear()
+
+
 class JetModel:
     """
     Class to handle physical model of an ionised jet from a young stellar object
@@ -494,19 +529,19 @@ class JetModel:
             self._log.add_entry(mtype="INFO",
                                 entry="Calculating cells' fill factors/projected areas")
         with torch.cuda.device(dev):
-            nverts = torch.empty(ncell, dtype=torch.uint8, device=dev)
-            cells = torch.empty((ncell, 2), dtype=torch.float64, device=dev)
+            m = self._model_struct()
+            nbricks = int(lib.rjp_brick_count(m))
+            nverts, cells, bricks = _take_state(torch, dev, ncell, nbricks)
             ties = torch.empty((_TIE_CAPACITY, 4), dtype=torch.int32, device=dev)
             counters = torch.zeros(8, dtype=torch.int32, device=dev)  # [0] n_ties
             nray = (self._x_hi - self._x_lo) * self._nz
             extents = torch.empty((nray, 2), dtype=torch.int32, device=dev)
             tie_cap = _TIE_CAPACITY
-            m = self._model_struct()
             for attempt in range(3):
                 counters.zero_()
                 st = lib.rjp_fill_grid(m, nverts.data_ptr(), cells.data_ptr(),
-                                       ties.data_ptr(), tie_cap, counters.data_ptr(),
-                                       extents.data_ptr(), self._stream())
+                                       bricks.data_ptr(), ties.data_ptr(), tie_cap,
+                                       counters.data_ptr(), extents.data_ptr(), self._stream())
                 _cabi.check(st, "rjp_fill_grid")
                 _launched()
                 c = counters.cpu().numpy()
@@ -517,7 +552,8 @@ class JetModel:
             else:
                 raise _cabi.EngineError("grid fill: tie list did not converge")
             n_ties = int(c[0])
-            self._dev = {"nverts": nverts, "cells": cells, "extents": extents, "model": m,
+            self._dev = {"nverts": nverts, "cells": cells, "bricks": bricks,
+                         "extents": extents, "model": m,
                          "device": dev, "stream2": torch.cuda.Stream(device=dev),
                          "n_ties": n_ties, "n_patched": 0}
             if n_ties > 0:
@@ -591,7 +627,8 @@ class JetModel:
         new8 = new.to(torch.uint8)
         st = lib.rjp_patch_cells(d["model"], idx.data_ptr(), new8.data_ptr(), idx.numel(),
                                  d["nverts"].data_ptr(), d["cells"].data_ptr(),
-                                 d["extents"].data_ptr(), self._stream())
+                                 d["bricks"].data_ptr(), d["extents"].data_ptr(),
+                                 self._stream())
         _cabi.check(st, "rjp_patch_cells")
         _launched()
 
@@ -619,8 +656,8 @@ class JetModel:
             new8 = torch.from_numpy(want[diff]).to(dev)
             st = lib.rjp_patch_cells(d["model"], idx.data_ptr(), new8.data_ptr(),
                                      idx.numel(), d["nverts"].data_ptr(),
-                                     d["cells"].data_ptr(), d["extents"].data_ptr(),
-                                     self._stream())
+                                     d["cells"].data_ptr(), d["bricks"].data_ptr(),
+                                     d["extents"].data_ptr(), self._stream())
             _cabi.check(st, "rjp_patch_cells")
         _launched()
         self._fields.clear()
@@ -743,6 +780,8 @@ class JetModel:
         self._invalidate()
 
     def _invalidate(self):
+        if self._dev is not None:
+            _give_state(self._dev)
         self._dev = None
         self._cont = None
         self._line = None

@@ -48,3 +48,52 @@ def test_sparse_walk_equals_dense_sweep(name):
         nz = a != 0
         assert np.abs(a[nz] / b[nz] - 1.0).max() < 1e-13, k
     assert torch.equal(jm._cont["cnt"], sparse["cnt"])
+
+
+def test_recycled_state_equals_dense_fill():
+    """The sparse fill on a recycled buffer (occupancy map of a DIFFERENT previous jet) must
+    leave exactly the state a dense fill writes into fresh memory."""
+    import copy
+    import torch
+    import rajepy_b200 as rb
+    from rajepy_b200 import _cabi, jetmodel
+    lib = _cabi.load()
+    log = rb.logger.Log(os.path.join(tempfile.mkdtemp(), "m.log"), verbose=False)
+    jetmodel.clear_state_pool()
+    pa = cases.with_grid(cases.base_params(), 72, 80, 96)
+    pb = copy.deepcopy(pa)
+    pb["geometry"].update({"inc": 55., "pa": 40., "opang": 40., "w_0": 2.0})
+    first = rb.JetModel(pa, log=log)
+    first._ensure_filled()
+    first.release()                       # buffers + occupancy map go to the pool
+    assert len(jetmodel._STATE_POOL) == 1
+    second = rb.JetModel(pb, log=log)
+    d = second._ensure_filled()           # recycled: zeroes stale bricks, writes new ones
+    assert len(jetmodel._STATE_POOL) == 0
+    ncell = d["nverts"].numel()
+    nv = torch.full((ncell,), 0xAB, dtype=torch.uint8, device="cuda")
+    cl = torch.full((ncell, 2), float("nan"), dtype=torch.float64, device="cuda")
+    ext = torch.empty_like(d["extents"])
+    ties = torch.empty((1 << 16, 4), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(8, dtype=torch.int32, device="cuda")
+    st = lib.rjp_fill_grid(d["model"], nv.data_ptr(), cl.data_ptr(), None, ties.data_ptr(),
+                           1 << 16, cnt.data_ptr(), ext.data_ptr(), second._stream())
+    _cabi.check(st, "rjp_fill_grid(dense)")
+    torch.cuda.synchronize()
+    if d["n_patched"] == 0:
+        assert torch.equal(nv, d["nverts"])
+        assert torch.equal(cl.view(torch.int64), d["cells"].view(torch.int64))
+        assert torch.equal(ext, d["extents"])
+    # occupancy map is consistent with the data: bricks marked empty hold only zeros
+    bricks = d["bricks"].cpu().numpy()
+    nxs, ny, nz = second._x_hi - second._x_lo, second._ny, second._nz
+    occ = (d["nverts"].view(nxs, ny, nz) != 0).cpu().numpy()
+    tx, ty, tz = 4, 8, 32
+    bx, by, bz = -(-nxs // tx), -(-ny // ty), -(-nz // tz)
+    pad = np.zeros((bx * tx, by * ty, bz * tz), dtype=bool)
+    pad[:nxs, :ny, :nz] = occ
+    per_brick = pad.reshape(bx, tx, by, ty, bz, tz).any(axis=(1, 3, 5)).reshape(-1)
+    assert bricks.size == per_brick.size
+    assert not np.any(per_brick & (bricks == 0))
+    second.release()
+    jetmodel.clear_state_pool()

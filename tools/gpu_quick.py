@@ -27,6 +27,9 @@ def timed(fn, n=3):
     return best
 
 
+SPARSE = "--dense-fill" not in sys.argv
+
+
 def main():
     argv = sys.argv[1:]
     nchan = 256
@@ -52,6 +55,7 @@ def main():
             cnt = torch.zeros(8, dtype=torch.int32, device="cuda")
             ties = torch.empty((1 << 16, 4), dtype=torch.int32, device="cuda")
             lib.rjp_fill_grid(d["model"], d["nverts"].data_ptr(), d["cells"].data_ptr(),
+                              d["bricks"].data_ptr() if SPARSE else None,
                               ties.data_ptr(), 1 << 16, cnt.data_ptr(),
                               d["extents"].data_ptr(), jm._stream())
         t_fill = timed(refill)
