@@ -543,7 +543,7 @@ class JetModel:
                                        bricks.data_ptr(), ties.data_ptr(), tie_cap,
                                        counters.data_ptr(), extents.data_ptr(), self._stream())
                 _cabi.check(st, "rjp_fill_grid")
-                _launched()
+                _launched(2)   # init_extents_kernel + fill_grid_kernel
                 c = counters.cpu().numpy()
                 if c[0] <= tie_cap:
                     break
@@ -869,7 +869,7 @@ class JetModel:
                                        self._stream(), d["stream2"].cuda_stream)
                 del keep
             _cabi.check(st, "rjp_integrate")
-            _launched(1 if line is None else 2 + (len(freqs) + 2047) // 2048)
+            _launched(2 if line is None else 1 + (len(freqs) + 2047) // 2048)
         self._cont = {"key": key_c, "em": em, "kff": kff, "tsum": tsum, "cnt": cnt}
         if line is None:
             return self._cont

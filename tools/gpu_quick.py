@@ -71,6 +71,15 @@ def main():
             jm._line = None
             jm._pass('H58a', chans, contsub=False)
         t_line = timed(line, 3)
+        if hasattr(lib, "rjp_debug_stamps"):
+            import ctypes
+            buf = (ctypes.c_ulonglong * 4)()
+            lib.rjp_debug_stamps(buf)
+            line()
+            lib.rjp_debug_stamps(buf)
+            t0 = min(buf[0], buf[2])
+            print(f"  stamps [us]: line kernel {(buf[0] - t0) / 1e3:.0f}..{(buf[1] - t0) / 1e3:.0f}, "
+                  f"missed kernel {(buf[2] - t0) / 1e3:.0f}..{(buf[3] - t0) / 1e3:.0f}")
         gb = ncell * 16 / 1e9
         print(f"n={n} cells={ncell:.3e} in-jet={injet} ({100 * injet / ncell:.2f}%) "
               f"ties={d['n_ties']} patched={d['n_patched']} first-fill wall {wall_fill:.2f}s\n"
