@@ -59,22 +59,39 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler is
+    started before the warm-up (nvidia-smi needs ~100 ms to come up) and only the samples whose
+    timestamps fall between mark_start() and mark_stop() are kept."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.path = os.path.join(tempfile.mkdtemp(), "clocks.csv")
         self.proc = None
+        self.t0 = self.t1 = None
         try:
             self.f = open(self.path, "wt")
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "20"],
+                 "--format=csv,noheader,nounits", "-lms", "10"],
                 stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def _stamp(txt):
+        import datetime
+        try:
+            return datetime.datetime.strptime(txt.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def stop(self):
         if self.proc is None:
@@ -85,24 +102,33 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc.kill()
         self.f.close()
-        sm, smax, reasons = [], [], set()
+        sm, smax, reasons, sm_all = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         with open(self.path) as f:
             for ln in f:
                 parts = [p.strip() for p in ln.split(",")]
-                if len(parts) < 7:
+                if len(parts) < 8:
                     continue
                 try:
-                    sm.append(float(parts[0]))
-                    smax.append(float(parts[1]))
+                    clk, cmax = float(parts[1]), float(parts[2])
                 except ValueError:
                     continue
-                for nm, v in zip(names, parts[3:7]):
+                sm_all.append(clk)
+                smax.append(cmax)
+                ts = self._stamp(parts[0])
+                inside = ts is not None and self.t0 is not None and self.t1 is not None and \
+                    self.t0 - 0.005 <= ts <= self.t1 + 0.005
+                if not inside:
+                    continue
+                sm.append(clk)
+                for nm, v in zip(names, parts[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_whole_run": len(sm_all),
+                "sm_mhz_whole_run": statistics.median(sm_all) if sm_all else None,
+                "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------- CPU arm
@@ -230,13 +256,15 @@ def run_gpu(args):
         jm.release()
         return s_ff.nbytes + t_l.nbytes + s_l.nbytes, float(np.nansum(s_l[len(chans) // 2]))
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         out = device_step()
         del out
     kernel_ms.clear()
     launches0 = jmod.LAUNCHES["count"]
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
+    if sampler:
+        sampler.mark_start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -244,6 +272,8 @@ def run_gpu(args):
         del out
     ev1.record()
     barrier()
+    if sampler:
+        sampler.mark_stop()
     clocks = sampler.stop() if sampler else None
     launches = jmod.LAUNCHES["count"] - launches0
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
@@ -324,7 +354,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=1024)
