@@ -431,6 +431,50 @@ __device__ inline void vt_cell_constants(double y, FastEntry& e) {
   e.xc2_hi = __double2hiint(fmin(fmax(x2 * K * K, RJP_VT_XWING2), RJP_VT_XCORE2 - 0.01));
 }
 
+// Packed fp32 pairs (sm_100 FFMA2: two FMAs per issue slot -- the channel loop is issue-bound)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// P(U) for two channels at once (same cell): same arithmetic as vt_wing_poly per half
+struct WingCoef2 { f32x2 g6, g5, c4, c3, c2, c1, one; };
+__device__ __forceinline__ WingCoef2 vt_wing_coef2(const FastEntry& e) {
+  constexpr float g1[] = {RJP_VT_G1};
+  WingCoef2 w;
+  w.g6 = pk2(g1[6], g1[6]);
+  w.g5 = pk2(g1[5], g1[5]);
+  w.c4 = pk2(e.c4, e.c4);
+  w.c3 = pk2(e.c3, e.c3);
+  w.c2 = pk2(e.c2, e.c2);
+  w.c1 = pk2(e.c1, e.c1);
+  w.one = pk2(1.0f, 1.0f);
+  return w;
+}
+__device__ __forceinline__ f32x2 vt_wing_poly2(const WingCoef2& w, f32x2 u) {
+  f32x2 p = fma2(w.g6, u, w.g5);
+  p = fma2(p, u, w.c4);
+  p = fma2(p, u, w.c3);
+  p = fma2(p, u, w.c2);
+  p = fma2(p, u, w.c1);
+  return fma2(p, u, w.one);
+}
+
 // wings: K = y kappa^2 G1(0) U P(U), U = 1 / X^2; this is P (fp32), U stays in fp64
 __device__ __forceinline__ float vt_wing_poly(const FastEntry& e, float u) {
   constexpr float g1[] = {RJP_VT_G1};

@@ -467,12 +467,13 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   // 32 neighbouring channels, i.e. nearly the same point of the line profile, so the
   // core / wing branches below are (almost always) warp-uniform
   double dn[GCH];
-  float dnf[GCH];
+  f32x2 dnf2[GCH / 2];
+  static_assert(GCH % 2 == 0, "channels are processed in pairs");
 #pragma unroll
-  for (int j = 0; j < GCH; ++j) {
+  for (int j = 0; j < GCH; ++j)
     dn[j] = (g + j * NT < nchan) ? __ldg(ch.dnu + g + j * NT) : 0.0;
-    dnf[j] = (float)dn[j];
-  }
+#pragma unroll
+  for (int j = 0; j < GCH; j += 2) dnf2[j >> 1] = pk2((float)dn[j], (float)dn[j + 1]);
   double acc[GCH];
 #pragma unroll
   for (int j = 0; j < GCH; ++j) acc[j] = 0.0;
@@ -531,40 +532,37 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
     // thread); channels inside the Gaussian core replace it by the table evaluation.
     for (int i = 0; i < nf; ++i) {
       const FastEntry fe = s_fast[i];
+      const WingCoef2 wc = vt_wing_coef2(fe);
+      const f32x2 b1 = pk2(fe.b1, fe.b1), b2 = pk2(fe.b2, fe.b2);
 #pragma unroll
-      for (int j = 0; j < GCH; ++j) {
-        const double X = fma(dn[j], fe.inv, fe.xs);
-        const double X2 = X * X;
-#if RJP_VARIANT == 1
-        double lead;
-        float kf;
-        if (__double2hiint(X2) < fe.xc2_hi) {
-          kf = vt_core(fe, tab, X, X2);
-          lead = fe.a0;
-        } else {
-          const double r0 = rcp_seed(X2);
-          lead = fe.w0 * (r0 * fma(-X2, r0, 2.0));
-          kf = vt_wing_poly(fe, d2f_trunc_pos(r0));
+      for (int j = 0; j < GCH; j += 2) {
+        // two channels per step: the fp32 work runs as packed FFMA2
+        const double Xa = fma(dn[j], fe.inv, fe.xs), Xb = fma(dn[j + 1], fe.inv, fe.xs);
+        const double X2a = Xa * Xa, X2b = Xb * Xb;
+        const double ra = rcp_seed(X2a), rb = rcp_seed(X2b);
+        double leada = fe.w0 * (ra * fma(-X2a, ra, 2.0));
+        double leadb = fe.w0 * (rb * fma(-X2b, rb, 2.0));
+        f32x2 k2 = vt_wing_poly2(wc, pk2(d2f_trunc_pos(ra), d2f_trunc_pos(rb)));
+        const bool corea = __double2hiint(X2a) < fe.xc2_hi, coreb = __double2hiint(X2b) < fe.xc2_hi;
+        if (corea || coreb) {
+          float ka, kb;
+          upk2(k2, ka, kb);
+          if (corea) {
+            ka = vt_core(fe, tab, Xa, X2a);
+            leada = fe.a0;
+          }
+          if (coreb) {
+            kb = vt_core(fe, tab, Xb, X2b);
+            leadb = fe.a0;
+          }
+          k2 = pk2(ka, kb);
         }
-#elif RJP_VARIANT == 2
-        const double r0 = rcp_seed(X2);
-        double lead = fe.w0 * (r0 * fma(-X2, r0, 2.0));
-        float kf = vt_wing_poly(fe, d2f_trunc_pos(r0));
-        if (__double2hiint(X2) < fe.xc2_hi) {
-          kf = vt_core_call(fe.yy, fe.y2f, fe.yf, fe.ya, tab, X, X2);
-          lead = fe.a0;
-        }
-#else
-        const double r0 = rcp_seed(X2);
-        double lead = fe.w0 * (r0 * fma(-X2, r0, 2.0));
-        float kf = vt_wing_poly(fe, d2f_trunc_pos(r0));
-        if (__double2hiint(X2) < fe.xc2_hi) {
-          kf = vt_core(fe, tab, X, X2);
-          lead = fe.a0;
-        }
-#endif
-        const float eps = dnf[j] * fmaf(dnf[j], fe.b2, fe.b1);
-        acc[j] = fma(lead, f2d_pos(fmaf(kf, eps, kf)), acc[j]);
+        const f32x2 d2 = dnf2[j >> 1];
+        const f32x2 eps = mul2(d2, fma2(d2, b2, b1));
+        float ka, kb;
+        upk2(fma2(k2, eps, k2), ka, kb);
+        acc[j] = fma(leada, f2d_pos(ka), acc[j]);
+        acc[j + 1] = fma(leadb, f2d_pos(kb), acc[j + 1]);
       }
     }
 
