@@ -52,6 +52,9 @@ constexpr int RPW = 8;          // rows in flight per warp
 #ifndef RJP_MINB64
 #define RJP_MINB64 8
 #endif
+#ifndef RJP_MINB128
+#define RJP_MINB128 4
+#endif
 constexpr int GCH = RJP_GCH;    // channels per thread of the line kernel
 constexpr int LINE_THREADS = 256;
 
@@ -539,11 +542,11 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
         // two channels per step: the fp32 work runs as packed FFMA2
         const double Xa = fma(dn[j], fe.inv, fe.xs), Xb = fma(dn[j + 1], fe.inv, fe.xs);
         const double X2a = Xa * Xa, X2b = Xb * Xb;
+        const bool corea = __double2hiint(X2a) < fe.xc2_hi, coreb = __double2hiint(X2b) < fe.xc2_hi;
         const double ra = rcp_seed(X2a), rb = rcp_seed(X2b);
         double leada = fe.w0 * (ra * fma(-X2a, ra, 2.0));
         double leadb = fe.w0 * (rb * fma(-X2b, rb, 2.0));
         f32x2 k2 = vt_wing_poly2(wc, pk2(d2f_trunc_pos(ra), d2f_trunc_pos(rb)));
-        const bool corea = __double2hiint(X2a) < fe.xc2_hi, coreb = __double2hiint(X2b) < fe.xc2_hi;
         if (corea || coreb) {
           float ka, kb;
           upk2(k2, ka, kb);
@@ -726,7 +729,7 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
                          pct);
     cudaFuncSetAttribute(integrate_line_kernel<64, RJP_MINB64>,
                          cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(integrate_line_kernel<128, 4>,
+    cudaFuncSetAttribute(integrate_line_kernel<128, RJP_MINB128>,
                          cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(integrate_line_kernel<LINE_THREADS, 2>,
                          cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -768,7 +771,7 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
             *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, em_o, kff, tsum, tcount,
             t_out, f_out);
       else if (threads <= 128)
-        integrate_line_kernel<128, 4><<<(unsigned)n_active, threads, 0, ls>>>(
+        integrate_line_kernel<128, RJP_MINB128><<<(unsigned)n_active, threads, 0, ls>>>(
             *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, em_o, kff, tsum, tcount,
             t_out, f_out);
       else
