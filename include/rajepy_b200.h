@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RJP_ABI_VERSION 2
+#define RJP_ABI_VERSION 3
 #define RJP_MAX_BURSTS 16
 
 enum {
@@ -204,6 +204,10 @@ int rjp_ray_list(const int32_t* extents, int64_t nray, int32_t* list, int32_t* n
  *   line/ch may be NULL/nchan = 0 for a continuum-only pass; otherwise
  *   tau_rrl and/or flux_rrl ([nchan][nxs][nz] double) may each be NULL.
  *   contsub: 0 -> flux_rrl includes S_ff (what Pipeline requests, classes.py:2450).
+ *   cube_plane / cube_offset: 0 / 0 -> the cubes are slab tiles [nchan][nxs*nz]; otherwise
+ *   ray i of the slab is element cube_offset + i of every plane of cube_plane elements, so
+ *   a slab can write straight into its rows of a full-size [nchan][nx*nz] cube
+ *   (cube_plane = nx*nz, cube_offset = x_lo*nz).
  * On return all work is ordered on `stream` (stream2 is joined back).              */
 int rjp_integrate(const rjp_model* m_host, const rjp_epoch* ep_host,
                   const rjp_continuum* cont_host, const rjp_cell* cells,
@@ -211,7 +215,23 @@ int rjp_integrate(const rjp_model* m_host, const rjp_epoch* ep_host,
                   double* em, double* kff, double* tsum,
                   int32_t* tcount, const rjp_line* line_host, const rjp_channels* ch_host,
                   int32_t nchan, int32_t contsub, double* tau_rrl, double* flux_rrl,
-                  void* stream, void* stream2);
+                  int64_t cube_plane, int64_t cube_offset, void* stream, void* stream2);
+
+/* Sparse exchange of cube tiles between x-slabs (multi-GPU): 94 % of the rays
+ * of the BASELINE jet miss the jet and carry constants (tau_L = 0, flux = NaN) that every rank
+ * can write itself once it knows the extents, so only the columns of jet-crossing rays travel.
+ *   rjp_pack_rays    out[c * n_stride + k] = cube[c * cube_plane + ray_ids[k]],  k < n
+ *   rjp_scatter_rays cube[c * cube_plane + ray_ids[k]] = in[c * n_stride + k]
+ *   rjp_fill_missed  for the nray rays described by `extents` (any slab's, e.g. all-gathered):
+ *                    tau = 0 / flux = NaN in every channel plane where the extent is empty;
+ *                    ray i is element cube_offset + i of a plane.  tau or flux may be NULL.
+ * ray_ids index into a plane (global ray = x * nz + z for a full-size cube).          */
+int rjp_pack_rays(const double* cube, int64_t cube_plane, const int32_t* ray_ids, int32_t n,
+                  int32_t n_stride, int32_t nchan, double* out, void* stream);
+int rjp_scatter_rays(const double* in, int32_t n_stride, const int32_t* ray_ids, int32_t n,
+                     int32_t nchan, double* cube, int64_t cube_plane, void* stream);
+int rjp_fill_missed(const int32_t* extents, int64_t nray, int32_t nchan, int64_t cube_plane,
+                    int64_t cube_offset, double* tau, double* flux, void* stream);
 
 /* Continuum epilogue (K5) for nfreq frequencies from one pass' kff/tsum/tcount:
  *   tau[f] = cff[f] * kff;  I[f] = iff[f] * Tmean * (1 - exp(-tau));  S[f] = I * omega_jy

@@ -62,7 +62,8 @@ _lib = None
 
 EXPORTS = ("rjp_strerror", "rjp_last_cuda_error", "rjp_abi_version", "rjp_struct_sizes",
            "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field", "rjp_ray_list", "rjp_integrate",
-           "rjp_continuum_images", "rjp_voigt_profile", "rjp_brick_count")
+           "rjp_continuum_images", "rjp_voigt_profile", "rjp_brick_count", "rjp_pack_rays",
+           "rjp_scatter_rays", "rjp_fill_missed")
 
 
 def library_path():
@@ -103,11 +104,15 @@ def load():
     lib.rjp_ray_list.argtypes = [vp, i64, vp, vp, vp]
     lib.rjp_integrate.argtypes = [C.POINTER(Model), C.POINTER(Epoch), C.POINTER(Continuum),
                                   vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(Line),
-                                  C.POINTER(Channels), i32, i32, vp, vp, vp, vp]
+                                  C.POINTER(Channels), i32, i32, vp, vp, i64, i64, vp, vp]
+    lib.rjp_pack_rays.argtypes = [vp, i64, vp, i32, i32, i32, vp, vp]
+    lib.rjp_scatter_rays.argtypes = [vp, i32, vp, i32, i32, vp, i64, vp]
+    lib.rjp_fill_missed.argtypes = [vp, i64, i32, i64, i64, vp, vp, vp]
     lib.rjp_continuum_images.argtypes = [vp, vp, vp, i64, vp, vp, dbl, i32, vp, vp, vp, vp]
     lib.rjp_voigt_profile.argtypes = [vp, vp, i64, vp, vp]
     for f in ("rjp_struct_sizes", "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field",
-              "rjp_ray_list", "rjp_integrate", "rjp_continuum_images", "rjp_voigt_profile"):
+              "rjp_ray_list", "rjp_integrate", "rjp_continuum_images", "rjp_voigt_profile",
+              "rjp_pack_rays", "rjp_scatter_rays", "rjp_fill_missed"):
         getattr(lib, f).restype = C.c_int
     sizes = [i32() for _ in range(6)]
     lib.rjp_struct_sizes(*[C.byref(s) for s in sizes])

@@ -16,7 +16,14 @@ int rjp_launch_field(const rjp_model*, const rjp_epoch*, const uint8_t*, int32_t
 int rjp_launch_integrate(const rjp_model*, const rjp_epoch*, const rjp_continuum*,
                          const rjp_cell*, const int32_t*, const int32_t*, int, double*, double*,
                          double*, int32_t*, const rjp_line*, const rjp_channels*, int, int,
-                         double, double*, double*, cudaStream_t, cudaStream_t);
+                         double, double*, double*, long long, long long, cudaStream_t,
+                         cudaStream_t);
+int rjp_launch_fill_missed(const int32_t*, long long, int, long long, long long, double*, double*,
+                           cudaStream_t);
+int rjp_launch_pack_rays(const double*, long long, const int32_t*, int, int, int, double*,
+                         cudaStream_t);
+int rjp_launch_scatter_rays(const double*, int, const int32_t*, int, int, double*, long long,
+                            cudaStream_t);
 int rjp_launch_ray_list(const int32_t*, int, int32_t*, int32_t*, cudaStream_t);
 int rjp_launch_continuum_images(const double*, const double*, const int32_t*, int64_t,
                                 const double*, const double*, double, int, double*, double*,
@@ -116,7 +123,8 @@ extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_
                              const int32_t* ray_list, int32_t n_active, double* em,
                              double* kff, double* tsum, int32_t* tcount, const rjp_line* ln,
                              const rjp_channels* ch, int32_t nchan, int32_t contsub,
-                             double* tau_rrl, double* flux_rrl, void* stream, void* stream2) {
+                             double* tau_rrl, double* flux_rrl, int64_t cube_plane,
+                             int64_t cube_offset, void* stream, void* stream2) {
   if (!model_ok(m) || !ep || !ct || !cells || !em || !kff || !tsum || !tcount || nchan < 0)
     return RJP_ERR_ARG;
   if (ep->n_blue < 0 || ep->n_blue > RJP_MAX_BURSTS || ep->n_red < 0 ||
@@ -127,12 +135,13 @@ extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_
       return RJP_ERR_ARG;
     if (!tau_rrl && !flux_rrl) return RJP_ERR_ARG;
     if (!extents || n_active < 0 || (n_active > 0 && !ray_list)) return RJP_ERR_ARG;
+    if (cube_plane < 0 || cube_offset < 0) return RJP_ERR_ARG;
   }
   return check_launch(rjp_launch_integrate(m, ep, ct, cells, extents, ray_list, n_active, em,
                                            kff, tsum, tcount,
                                            ln, ch, nchan, contsub, ln ? ln->dn_max : 0.0,
-                                           tau_rrl, flux_rrl, (cudaStream_t)stream,
-                                           (cudaStream_t)stream2));
+                                           tau_rrl, flux_rrl, cube_plane, cube_offset,
+                                           (cudaStream_t)stream, (cudaStream_t)stream2));
 }
 
 extern "C" int rjp_continuum_images(const double* kff, const double* tsum,
@@ -151,4 +160,32 @@ extern "C" int rjp_voigt_profile(const double* x, const double* y, int64_t n, do
                                  void* stream) {
   if (n < 0 || (n > 0 && (!x || !y || !out))) return RJP_ERR_ARG;
   return check_launch(rjp_launch_voigt_profile(x, y, n, out, (cudaStream_t)stream));
+}
+
+extern "C" int rjp_fill_missed(const int32_t* extents, int64_t nray, int32_t nchan,
+                               int64_t cube_plane, int64_t cube_offset, double* tau, double* flux,
+                               void* stream) {
+  if (nray < 0 || nchan < 0 || (nray > 0 && !extents) || cube_plane < cube_offset + nray ||
+      cube_offset < 0 || (!tau && !flux))
+    return RJP_ERR_ARG;
+  return check_launch(rjp_launch_fill_missed(extents, nray, nchan, cube_plane, cube_offset, tau,
+                                             flux, (cudaStream_t)stream));
+}
+
+extern "C" int rjp_pack_rays(const double* cube, int64_t cube_plane, const int32_t* ray_ids,
+                             int32_t n, int32_t n_stride, int32_t nchan, double* out,
+                             void* stream) {
+  if (n < 0 || nchan < 0 || n_stride < n || (n > 0 && nchan > 0 && (!cube || !ray_ids || !out)))
+    return RJP_ERR_ARG;
+  return check_launch(rjp_launch_pack_rays(cube, cube_plane, ray_ids, n, n_stride, nchan, out,
+                                           (cudaStream_t)stream));
+}
+
+extern "C" int rjp_scatter_rays(const double* in, int32_t n_stride, const int32_t* ray_ids,
+                                int32_t n, int32_t nchan, double* cube, int64_t cube_plane,
+                                void* stream) {
+  if (n < 0 || nchan < 0 || n_stride < n || (n > 0 && nchan > 0 && (!cube || !ray_ids || !in)))
+    return RJP_ERR_ARG;
+  return check_launch(rjp_launch_scatter_rays(in, n_stride, ray_ids, n, nchan, cube, cube_plane,
+                                              (cudaStream_t)stream));
 }

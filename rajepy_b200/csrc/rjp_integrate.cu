@@ -330,10 +330,12 @@ __global__ void __maxnreg__(32)
 missed_rays_kernel(const int2* __restrict__ extents, size_t nray, int nchan,
                    double* __restrict__ em, double* __restrict__ kff,
                    double* __restrict__ tsum, int32_t* __restrict__ tcount,
-                   double* __restrict__ tau, double* __restrict__ flux) {
+                   double* __restrict__ tau, double* __restrict__ flux, size_t plane,
+                   size_t offset) {
   // persistent: a warp takes 128 consecutive rays at a time (4 per lane) and loops over the
-  // channel planes -- no loads inside the store stream; one light CTA per SM leaves the rest
-  // of the SM to the channel loop
+  // channel planes -- no loads inside the store stream; a light grid leaves the SMs to the
+  // channel loop.  Ray i of `extents` is element offset + i of every cube plane (plane =
+  // elements per plane): a slab writes into its rows of a full-size cube this way.
   RJP_STAMP_BEGIN(1)
   const int lane = threadIdx.x & 31;
   const size_t gw = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -350,7 +352,7 @@ missed_rays_kernel(const int2* __restrict__ extents, size_t nray, int nchan,
         const int2 e = __ldg(extents + ray);
         miss[k] = e.x >= e.y;
       }
-      if (miss[k]) {
+      if (miss[k] && em != nullptr) {
         em[ray] = 0.0;
         kff[ray] = 0.0;
         tsum[ray] = 0.0;
@@ -360,7 +362,7 @@ missed_rays_kernel(const int2* __restrict__ extents, size_t nray, int nchan,
     }
     if (!any) continue;
     for (int c = 0; c < nchan; ++c) {
-      const size_t o = (size_t)c * nray + r0 + lane;
+      const size_t o = (size_t)c * plane + offset + r0 + lane;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (miss[k]) {
@@ -371,6 +373,31 @@ missed_rays_kernel(const int2* __restrict__ extents, size_t nray, int nchan,
     }
   }
   RJP_STAMP_END(1)
+}
+
+// Sparse tile exchange between slabs (multi-GPU): only the cube columns of jet-crossing rays
+// travel.  pack: out[c][k] = cube[c][ray_ids[k]]; scatter: the inverse.  Lanes run along k;
+// with a sorted ray list neighbouring k are neighbouring rays, so both sides coalesce.
+__global__ void pack_rays_kernel(const double* __restrict__ cube, size_t plane,
+                                 const int32_t* __restrict__ ray_ids, int n, int n_stride,
+                                 int nchan, double* __restrict__ out) {
+  const size_t total = (size_t)n * nchan;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i / n), k = (int)(i - (size_t)c * n);
+    out[(size_t)c * n_stride + k] = cube[(size_t)c * plane + ray_ids[k]];
+  }
+}
+
+__global__ void scatter_rays_kernel(const double* __restrict__ in, int n_stride,
+                                    const int32_t* __restrict__ ray_ids, int n, int nchan,
+                                    double* __restrict__ cube, size_t plane) {
+  const size_t total = (size_t)n * nchan;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i / n), k = (int)(i - (size_t)c * n);
+    cube[(size_t)c * plane + ray_ids[k]] = in[(size_t)c * n_stride + k];
+  }
 }
 
 // Continuum-only walk: one warp per jet-crossing ray, lanes stride along the extent.
@@ -439,7 +466,8 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
                       const int32_t* __restrict__ ray_list, double* __restrict__ em,
                       double* __restrict__ kff, double* __restrict__ tsum,
                       int32_t* __restrict__ tcount, double* __restrict__ tau_rrl,
-                      double* __restrict__ flux_rrl) {
+                      double* __restrict__ flux_rrl, const size_t plane,
+                      const size_t cube_offset) {
   __shared__ Params s_p;
   __shared__ rjp_line s_ln;
   // one batch of prepared cells: fast-class entries from the front, the others behind them
@@ -463,7 +491,6 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   const int ray = ray_list[blockIdx.x];          // slab-local ray index = xl * nz + iz
   const int xl = ray / m.nz, iz = ray - xl * m.nz;
   const int ix = m.x_lo + xl;
-  const size_t plane = (size_t)(m.x_hi - m.x_lo) * m.nz;
   const int2 ext = extents[ray];
 
   // thread g owns channels g, g + NT, g + 2 NT, ...: at every step the lanes of a warp hold
@@ -627,7 +654,7 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   for (int j = 0; j < GCH; ++j) {
     const int c = g + j * NT;
     if (c >= nchan) break;
-    if (tau_rrl) tau_rrl[(size_t)c * plane + ray] = acc[j];
+    if (tau_rrl) tau_rrl[(size_t)c * plane + cube_offset + ray] = acc[j];
     if (flux_rrl) {
       double s = dnan();
       if (cn > 0) {
@@ -637,7 +664,7 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
         s = bnu * ec * (1.0 - exp(-acc[j]));
         if (!contsub) s += __ldg(ch.aff + c) * (tmean * (1.0 - ec));
       }
-      flux_rrl[(size_t)c * plane + ray] = s;
+      flux_rrl[(size_t)c * plane + cube_offset + ray] = s;
     }
   }
   RJP_STAMP_END(0)
@@ -694,6 +721,25 @@ extern "C" int rjp_launch_ray_list(const int32_t* extents, int nray, int32_t* li
   return RJP_OK;
 }
 
+// Same shared-memory carve-out for the kernels that are meant to be co-resident: an SM only
+// switches its L1 / shared split when it is idle, so a kernel that asks for a different split
+// waits until the other one has drained (measured: the channel loop started 0.9 ms late
+// behind the constant writer, which uses no shared memory).
+static void set_carveouts() {
+  static bool done = false;
+  if (done) return;
+  const int pct = 50;
+  cudaFuncSetAttribute(missed_rays_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(continuum_rays_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(integrate_line_kernel<64, RJP_MINB64>,
+                       cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(integrate_line_kernel<128, RJP_MINB128>,
+                       cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(integrate_line_kernel<LINE_THREADS, 2>,
+                       cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  done = true;
+}
+
 extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
                                     const rjp_continuum* ct, const rjp_cell* cells,
                                     const int32_t* extents, const int32_t* ray_list,
@@ -701,6 +747,7 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
                                     int32_t* tcount, const rjp_line* ln,
                                     const rjp_channels* ch, int nchan, int contsub,
                                     double dn_max, double* tau_rrl, double* flux_rrl,
+                                    long long cube_plane, long long cube_offset,
                                     cudaStream_t stream, cudaStream_t stream2) {
   const int nxs = m->x_hi - m->x_lo;
   const long long ctas = (long long)nxs * ((m->nz + ZT - 1) / ZT);
@@ -717,24 +764,10 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
     return RJP_OK;
   }
   const size_t nray = (size_t)nxs * m->nz;
-  // Same shared-memory carve-out for the kernels that are meant to be co-resident: an SM
-  // only switches its L1 / shared split when it is idle, so a kernel that asks for a
-  // different split waits until the other one has drained (measured: the channel loop
-  // started 0.9 ms late behind the constant writer, which uses no shared memory).
-  static bool carveout_set = false;
-  if (!carveout_set) {
-    const int pct = 50;
-    cudaFuncSetAttribute(missed_rays_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(continuum_rays_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                         pct);
-    cudaFuncSetAttribute(integrate_line_kernel<64, RJP_MINB64>,
-                         cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(integrate_line_kernel<128, RJP_MINB128>,
-                         cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(integrate_line_kernel<LINE_THREADS, 2>,
-                         cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    carveout_set = true;
-  }
+  const size_t plane = cube_plane > 0 ? (size_t)cube_plane : nray;
+  const size_t coff = cube_plane > 0 ? (size_t)cube_offset : 0;
+  if (plane < coff + nray) return RJP_ERR_ARG;
+  set_carveouts();
   cudaEvent_t fork = nullptr, join = nullptr;
   cudaStream_t ls = stream;
   if (n_active > 0 && stream2 != nullptr && stream2 != stream) {
@@ -751,7 +784,7 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
   // every other SM keeps 3.4 TB/s of stores in flight), launched first so that it is
   // resident beside the ray kernels; measured best of 74..1184 CTAs x 32..256 threads
   missed_rays_kernel<<<74, 64, 0, stream>>>(ex2, nray, lines ? nchan : 0, em, kff, tsum, tcount,
-                                            tau_rrl, flux_rrl);
+                                            tau_rrl, flux_rrl, plane, coff);
   if (lines && n_active > 0) {
     // channel blocks of at most 8 * 256 channels per launch; the first one also writes the
     // continuum images of its rays
@@ -761,7 +794,7 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
       const int threads = ((groups + 31) / 32) * 32;
       rjp_channels cb = *ch;
       cb.dnu += c0; cb.nu += c0; cb.cff += c0; cb.aff += c0; cb.bnu += c0;
-      const size_t off = (size_t)c0 * nray;
+      const size_t off = (size_t)c0 * plane;
       double* t_out = tau_rrl ? tau_rrl + off : nullptr;
       double* f_out = flux_rrl ? flux_rrl + off : nullptr;
       double* em_o = (c0 == 0) ? em : nullptr;
@@ -769,15 +802,15 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
       if (threads <= 64)
         integrate_line_kernel<64, RJP_MINB64><<<(unsigned)n_active, threads, 0, ls>>>(
             *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, em_o, kff, tsum, tcount,
-            t_out, f_out);
+            t_out, f_out, plane, coff);
       else if (threads <= 128)
         integrate_line_kernel<128, RJP_MINB128><<<(unsigned)n_active, threads, 0, ls>>>(
             *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, em_o, kff, tsum, tcount,
-            t_out, f_out);
+            t_out, f_out, plane, coff);
       else
         integrate_line_kernel<LINE_THREADS, 2><<<(unsigned)n_active, threads, 0, ls>>>(
             *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, em_o, kff, tsum, tcount,
-            t_out, f_out);
+            t_out, f_out, plane, coff);
     }
   } else if (n_active > 0) {
     continuum_rays_kernel<<<(n_active + 7) / 8, 256, 0, ls>>>(*m, *ep, *ct, c4, ex2, ray_list,
@@ -801,6 +834,38 @@ extern "C" int rjp_debug_stamps(unsigned long long* out4) {
   return 0;
 }
 #endif
+
+extern "C" int rjp_launch_fill_missed(const int32_t* extents, long long nray, int nchan,
+                                      long long plane, long long offset, double* tau,
+                                      double* flux, cudaStream_t stream) {
+  if (nray <= 0 || nchan <= 0) return RJP_OK;
+  set_carveouts();
+  // light grid: meant to run on a side stream beside the channel loop (multi-GPU: the
+  // constants of the OTHER slabs' rays)
+  missed_rays_kernel<<<148, 64, 0, stream>>>(reinterpret_cast<const int2*>(extents),
+                                                  (size_t)nray, nchan, nullptr, nullptr, nullptr,
+                                                  nullptr, tau, flux, (size_t)plane,
+                                                  (size_t)offset);
+  return RJP_OK;
+}
+
+extern "C" int rjp_launch_pack_rays(const double* cube, long long plane, const int32_t* ray_ids,
+                                    int n, int n_stride, int nchan, double* out,
+                                    cudaStream_t stream) {
+  if (n <= 0 || nchan <= 0) return RJP_OK;
+  pack_rays_kernel<<<148 * 8, 256, 0, stream>>>(cube, (size_t)plane, ray_ids, n, n_stride, nchan,
+                                                out);
+  return RJP_OK;
+}
+
+extern "C" int rjp_launch_scatter_rays(const double* in, int n_stride, const int32_t* ray_ids,
+                                       int n, int nchan, double* cube, long long plane,
+                                       cudaStream_t stream) {
+  if (n <= 0 || nchan <= 0) return RJP_OK;
+  scatter_rays_kernel<<<148 * 8, 256, 0, stream>>>(in, n_stride, ray_ids, n, nchan, cube,
+                                                   (size_t)plane);
+  return RJP_OK;
+}
 
 extern "C" int rjp_launch_voigt_profile(const double* x, const double* y, int64_t n,
                                         double* out, cudaStream_t stream) {

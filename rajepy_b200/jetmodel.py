@@ -578,7 +578,10 @@ class JetModel:
         _cabi.check(st, "rjp_ray_list")
         _launched()
         d["n_active"] = int(n_act.item())
-        d["rays"] = rays[:max(d["n_active"], 1)].clone()
+        # sorted: neighbouring CTAs of the ray kernels write neighbouring cube columns, and the
+        # sparse cube exchange between slabs packs / scatters coalesced
+        d["rays"] = torch.sort(rays[:max(d["n_active"], 1)])[0].contiguous()
+        d["ray_meta"] = None
 
     def _resolve_ties(self, ties):
         """Vertices whose inside test the device could not call: decide every
@@ -851,14 +854,19 @@ class JetModel:
                                        d["extents"].data_ptr(), d["rays"].data_ptr(),
                                        d["n_active"], em.data_ptr(), kff.data_ptr(),
                                        tsum.data_ptr(), cnt.data_ptr(), None, None, 0, 1,
-                                       None, None, self._stream(), None)
+                                       None, None, 0, 0, self._stream(), None)
             else:
                 ln, chans, keep = self._line_structs(line, freqs, dev)
                 nch = len(freqs)
+                # sharded: every rank writes its slab straight into full-size cubes; the
+                # other slabs arrive through the sparse exchange below
+                rows = self._nx if self._world > 1 else nxs
+                plane, coff = (self._nx * nz, self._x_lo * nz) if self._world > 1 else (0, 0)
                 if want_tau:
-                    tau = torch.empty((nch, nxs, nz), dtype=torch.float64, device=dev)
+                    tau = torch.empty((nch, rows, nz), dtype=torch.float64, device=dev)
                 if want_flux:
-                    flux = torch.empty((nch, nxs, nz), dtype=torch.float64, device=dev)
+                    flux = torch.empty((nch, rows, nz), dtype=torch.float64, device=dev)
+                side = self._fill_remote_constants(tau, flux) if self._world > 1 else None
                 st = lib.rjp_integrate(d["model"], ep, ct, d["cells"].data_ptr(),
                                        d["extents"].data_ptr(), d["rays"].data_ptr(),
                                        d["n_active"], em.data_ptr(), kff.data_ptr(),
@@ -866,7 +874,11 @@ class JetModel:
                                        chans, nch, 1 if contsub else 0,
                                        tau.data_ptr() if want_tau else None,
                                        flux.data_ptr() if want_flux else None,
+                                       plane, coff,
                                        self._stream(), d["stream2"].cuda_stream)
+                if self._world > 1:
+                    _cabi.check(st, "rjp_integrate")
+                    self._exchange_cubes(tau, flux, side)
                 del keep
             _cabi.check(st, "rjp_integrate")
             _launched(2 if line is None else 1 + (len(freqs) + 2047) // 2048)
@@ -913,6 +925,8 @@ class JetModel:
     def _host_image(self, t, lead=None):
         """Device tile(s) -> full host numpy array, all-gathering x-slabs if sharded."""
         nxs, nz = self._x_hi - self._x_lo, self._nz
+        if lead is not None and self._world > 1 and t.numel() == lead * self._nx * nz:
+            return _to_host(t.view(lead, self._nx, nz))      # cube completed by _exchange_cubes
         t = t.view(nxs, nz) if lead is None else t.view(lead, nxs, nz)
         if self._world > 1:
             t = gather_x(t, self._nx, self._rank, self._world, dim=0 if lead is None else 1)
@@ -970,8 +984,83 @@ class JetModel:
             out["flux_rrl"] = conv(res["flux"], lead=nch)
         return out
 
+    def _ray_meta(self):
+        from . import sharding
+        d = self._dev
+        if d.get("ray_meta") is None:
+            d["ray_meta"] = sharding.build_ray_meta(d["extents"], d["rays"][:d["n_active"]],
+                                                    self._x_lo, self._nx, self._nz, self._rank,
+                                                    self._world)
+        return d["ray_meta"]
+
+    def _fill_remote_constants(self, tau, flux):
+        """Sharded line pass: the constants (tau = 0, flux = NaN) of the OTHER slabs' rays that
+        miss the jet, from the all-gathered extents, on a side stream so that they are
+        written beside this slab's channel loop.  Returns the side stream."""
+        torch = _torch()
+        from . import sharding
+        lib = _cabi.load()
+        d = self._dev
+        nz, nx = self._nz, self._nx
+        meta = self._ray_meta()
+        if d.get("stream3") is None:
+            d["stream3"] = torch.cuda.Stream(device=d["device"])
+        side = d["stream3"]
+        side.wait_stream(torch.cuda.current_stream(d["device"]))
+        nch = (tau if tau is not None else flux).shape[0]
+        for r in range(self._world):
+            if r == self._rank:
+                continue
+            lo, hi = sharding.slab_bounds(nx, r, self._world)
+            ext = meta["extents"][lo * nz: hi * nz]
+            st = lib.rjp_fill_missed(ext.data_ptr(), ext.shape[0], nch, nx * nz, lo * nz,
+                                     tau.data_ptr() if tau is not None else None,
+                                     flux.data_ptr() if flux is not None else None,
+                                     side.cuda_stream)
+            _cabi.check(st, "rjp_fill_missed")
+            _launched()
+        return side
+
+    def _exchange_cubes(self, tau, flux, side):
+        """Sparse all-gather of the line cubes between x-slabs (sharding.exchange_ray_columns)
+        with the C-ABI pack / scatter kernels; the constants of the other slabs were written
+        by _fill_remote_constants on `side`."""
+        torch = _torch()
+        from . import sharding
+        lib = _cabi.load()
+        d = self._dev
+        nz, nx = self._nz, self._nx
+        stream = self._stream()
+        plane = nx * nz
+
+        class Ops:
+            @staticmethod
+            def pack(cube, ids, out):
+                _cabi.check(lib.rjp_pack_rays(cube.data_ptr(), plane, ids.data_ptr(), ids.numel(),
+                                              out.shape[1], out.shape[0], out.data_ptr(),
+                                              stream), "rjp_pack_rays")
+                _launched()
+
+            @staticmethod
+            def scatter(src, ids, cube):
+                _cabi.check(lib.rjp_scatter_rays(src.data_ptr(), src.shape[1], ids.data_ptr(),
+                                                 ids.numel(), src.shape[0], cube.data_ptr(),
+                                                 plane, stream), "rjp_scatter_rays")
+                _launched()
+
+            @staticmethod
+            def fill_missed(extents, offset, cubes, values):
+                pass    # done on the side stream, beside the channel loop
+
+        views = [c.view(c.shape[0], plane) if c is not None else None for c in (tau, flux)]
+        sharding.exchange_ray_columns(views, [0.0, float("nan")], self._ray_meta(), nx, nz,
+                                      self._rank, self._world, ops=Ops)
+        torch.cuda.current_stream(d["device"]).wait_stream(side)
+
     def _device_image(self, t, lead=None):
         nxs, nz = self._x_hi - self._x_lo, self._nz
+        if lead is not None and self._world > 1 and t.numel() == lead * self._nx * nz:
+            return t.view(lead, self._nx, nz)
         t = t.view(nxs, nz) if lead is None else t.view(lead, nxs, nz)
         if self._world > 1:
             t = gather_x(t, self._nx, self._rank, self._world, dim=0 if lead is None else 1)

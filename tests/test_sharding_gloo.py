@@ -75,3 +75,72 @@ def test_sharded_model_slabs_are_consistent():
     slabs = [rb.JetModel(cases.case_c1(), log=log, shard=(r, 8)).slab for r in range(8)]
     assert slabs[0][0] == 0 and slabs[-1][1] == 50
     assert all(slabs[i][1] == slabs[i + 1][0] for i in range(7))
+
+
+# ------------------------------------------------------------------ sparse cube exchange
+def _exchange_worker(rank, world, port, nx, nz, path, out_dir):
+    import torch
+    import torch.distributed as dist
+    from rajepy_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = np.load(path)
+    lo, hi = sharding.slab_bounds(nx, rank, world)
+    nch = d["tau"].shape[0]
+    # what a rank holds after its own pass: full-size cubes whose rows of the OWN slab are
+    # final, everything else uninitialised (poisoned here)
+    cubes = []
+    for name in ("tau", "flux"):
+        c = np.full((nch, nx, nz), 123.456)
+        c[:, lo:hi] = d[name][:, lo:hi]
+        cubes.append(torch.from_numpy(c).view(nch, nx * nz))
+    ext = torch.from_numpy(d["extents"][lo * nz: hi * nz].copy())
+    local_rays = torch.from_numpy(np.flatnonzero(d["extents"][lo * nz: hi * nz, 0] <
+                                                 d["extents"][lo * nz: hi * nz, 1])
+                                  .astype(np.int32))
+    local_rays = local_rays[torch.randperm(local_rays.numel())]   # the GPU list is unordered
+    meta = sharding.build_ray_meta(ext, local_rays, lo, nx, nz, rank, world)
+    assert sum(meta["counts"]) == int((d["extents"][:, 0] < d["extents"][:, 1]).sum())
+    sharding.exchange_ray_columns(cubes, [0.0, float("nan")], meta, nx, nz, rank, world)
+    # tau only (flux not requested)
+    only = torch.from_numpy(np.where(np.arange(nx)[None, :, None] // 1 >= 0, 7.0, 7.0) *
+                            np.ones((nch, nx, nz))).view(nch, nx * nz)
+    only.view(nch, nx, nz)[:, lo:hi] = torch.from_numpy(d["tau"][:, lo:hi])
+    sharding.exchange_ray_columns([only, None], [0.0, float("nan")], meta, nx, nz, rank, world)
+    np.savez(os.path.join(out_dir, f"x{rank}.npz"), tau=cubes[0].view(nch, nx, nz).numpy(),
+             flux=cubes[1].view(nch, nx, nz).numpy(), only=only.view(nch, nx, nz).numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sparse_cube_exchange(world):
+    """Only the cube columns of jet-crossing rays travel; every rank rebuilds the constants
+    of the other slabs from the all-gathered extents.  The result must be the full oracle
+    cube on every rank (18 planes over 4 ranks: uneven slabs)."""
+    import torch.multiprocessing as mp
+    from oracle import rajepy_oracle as orc
+    p = cases.with_grid(cases.base_params(), 18, 24, 30)
+    oj = orc.OracleJet(p)
+    nu0 = orc.rrl_nu_0('H', 58, 1)
+    chans = cases.line_channels(nu0, 5, 1e6)
+    tau = oj.optical_depth_rrl('H58a', chans)
+    flux = oj.flux_rrl('H58a', chans, contsub=False)
+    inside = oj.n_verts_inside() > 0                       # (nx, ny, nz)
+    any_in = inside.any(axis=1)
+    first = np.where(any_in, inside.argmax(axis=1), 2147483647)
+    last = np.where(any_in, inside.shape[1] - inside[:, ::-1].argmax(axis=1), 0)
+    extents = np.stack([first, last], axis=-1).reshape(-1, 2).astype(np.int32)
+    assert np.array_equal(np.isnan(flux[0]).reshape(-1), extents[:, 0] >= extents[:, 1])
+    tmp = tempfile.mkdtemp()
+    path = os.path.join(tmp, "in.npz")
+    np.savez(path, tau=tau, flux=flux, extents=extents)
+    mp.spawn(_exchange_worker, args=(world, _free_port(), oj.nx, oj.nz, path, tmp),
+             nprocs=world, join=True)
+    for r in range(world):
+        out = np.load(os.path.join(tmp, f"x{r}.npz"))
+        assert np.array_equal(out["tau"], tau)
+        assert np.array_equal(np.isnan(out["flux"]), np.isnan(flux))
+        assert np.array_equal(np.nan_to_num(out["flux"]), np.nan_to_num(flux))
+        assert np.array_equal(out["only"], tau)
