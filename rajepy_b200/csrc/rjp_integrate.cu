@@ -837,12 +837,13 @@ extern "C" int rjp_debug_stamps(unsigned long long* out4) {
 
 extern "C" int rjp_launch_fill_missed(const int32_t* extents, long long nray, int nchan,
                                       long long plane, long long offset, double* tau,
-                                      double* flux, cudaStream_t stream) {
+                                      double* flux, int light, cudaStream_t stream) {
   if (nray <= 0 || nchan <= 0) return RJP_OK;
   set_carveouts();
-  // light grid: meant to run on a side stream beside the channel loop (multi-GPU: the
-  // constants of the OTHER slabs' rays)
-  missed_rays_kernel<<<148, 64, 0, stream>>>(reinterpret_cast<const int2*>(extents),
+  // light grid: meant to run on a side stream beside a long channel loop (multi-GPU: the
+  // constants of the OTHER slabs' rays); otherwise a grid that reaches the HBM write peak
+  missed_rays_kernel<<<light ? 148 : 148 * 4, light ? 64 : 128, 0, stream>>>(
+      reinterpret_cast<const int2*>(extents),
                                                   (size_t)nray, nchan, nullptr, nullptr, nullptr,
                                                   nullptr, tau, flux, (size_t)plane,
                                                   (size_t)offset);

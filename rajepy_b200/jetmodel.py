@@ -25,7 +25,7 @@ import scipy.constants as con
 from . import _cabi
 from . import hostmath as hm
 from . import logger
-from .sharding import gather_x, slab_bounds
+from .sharding import balanced_bounds, even_bounds, gather_x
 
 _TIE_CAPACITY = 1 << 16
 
@@ -125,7 +125,7 @@ class JetModel:
             raise err
         return mod.params
 
-    def __init__(self, params, log=None, device=None, shard=None):
+    def __init__(self, params, log=None, device=None, shard=None, balance=True):
         if isinstance(params, dict):
             self._params = params
         elif isinstance(params, str):
@@ -202,7 +202,10 @@ class JetModel:
         if shard is None:
             shard = (0, 1)
         self._rank, self._world = int(shard[0]), int(shard[1])
-        self._x_lo, self._x_hi = slab_bounds(self._nx, self._rank, self._world)
+        # x-slabs of equal estimated work (in-jet cells), not equal width: see _plane_weights
+        self._bounds = balanced_bounds(self._plane_weights(), self._world) \
+            if (balance and self._world > 1) else even_bounds(self._nx, self._world)
+        self._x_lo, self._x_hi = self._bounds[self._rank]
         self._dev = None       # dict of device buffers once filled
         self._fields = {}      # cached host copies of 3-D property grids
         self._overrides = {}   # user-assigned grids (setters)
@@ -210,6 +213,28 @@ class JetModel:
         self._line = None      # cached line pass
         self._timings = {}
         self._coeff_cache = {}
+
+    def _plane_weights(self):
+        """Estimated number of in-jet cells of every x-plane from a coarse sample of cell
+        centres (classes.py:661-666 at the centroid): the work per plane of the sparse fill and
+        of the ray walk.  Pure function of the parameters, so every rank derives the same
+        slab boundaries without communicating."""
+        g = self._params["geometry"]
+        nx, ny, nz, cs = self._nx, self._ny, self._nz, self._csize
+        sx, sy, sz = max(1, nx // 256), max(1, ny // 96), max(1, nz // 96)
+        ix = np.arange(sx // 2, nx, sx)
+        iy = np.arange(sy // 2, ny, sy)
+        iz = np.arange(sz // 2, nz, sz)
+        x = cs * (ix - nx // 2 + 0.5)
+        y = cs * (iy - ny // 2 + 0.5)
+        z = cs * (iz - nz // 2 + 0.5)
+        xx, yy, zz = np.meshgrid(x, y, z, indexing="ij")
+        r, w, _ = hm.xyz_to_rwp(xx, yy, zz, g["inc"], g["pa"])
+        with np.errstate(all="ignore"):
+            inside = (w <= hm.w_r(r, g["w_0"], g["mod_r_0"], g["r_0"], g["epsilon"])) & \
+                     (np.abs(r) >= g["r_0"])
+        coarse = inside.sum(axis=(1, 2)).astype(np.float64)
+        return np.interp(np.arange(nx), ix, coarse)
 
     # ------------------------------------------------------------------ text table
     def __str__(self):
@@ -672,7 +697,7 @@ class JetModel:
         d = self._ensure_filled()
         t = d["nverts"].view(self._x_hi - self._x_lo, self._ny, self._nz)
         if gather and self._world > 1:
-            t = gather_x(t, self._nx, self._rank, self._world, dim=0)
+            t = gather_x(t, self._nx, self._rank, self._world, dim=0, bounds=self._bounds)
         return t.cpu().numpy()
 
     def _field_device(self, name):
@@ -696,7 +721,7 @@ class JetModel:
             return self._fields[name]
         t = self._field_device(name)
         if gather and self._world > 1:
-            t = gather_x(t, self._nx, self._rank, self._world, dim=0)
+            t = gather_x(t, self._nx, self._rank, self._world, dim=0, bounds=self._bounds)
         arr = t.cpu().numpy()
         if cache:
             self._fields[name] = arr
@@ -929,7 +954,8 @@ class JetModel:
             return _to_host(t.view(lead, self._nx, nz))      # cube completed by _exchange_cubes
         t = t.view(nxs, nz) if lead is None else t.view(lead, nxs, nz)
         if self._world > 1:
-            t = gather_x(t, self._nx, self._rank, self._world, dim=0 if lead is None else 1)
+            t = gather_x(t, self._nx, self._rank, self._world, dim=0 if lead is None else 1,
+                         bounds=self._bounds)
         return _to_host(t)
 
     def _continuum_images_device(self, freqs, want):
@@ -990,7 +1016,7 @@ class JetModel:
         if d.get("ray_meta") is None:
             d["ray_meta"] = sharding.build_ray_meta(d["extents"], d["rays"][:d["n_active"]],
                                                     self._x_lo, self._nx, self._nz, self._rank,
-                                                    self._world)
+                                                    self._world, bounds=self._bounds)
         return d["ray_meta"]
 
     def _fill_remote_constants(self, tau, flux):
@@ -1008,15 +1034,21 @@ class JetModel:
         side = d["stream3"]
         side.wait_stream(torch.cuda.current_stream(d["device"]))
         nch = (tau if tau is not None else flux).shape[0]
+        # beside a long channel loop a light store grid interferes least; when this slab's loop
+        # is shorter than the constant fill itself, the fill should run at full bandwidth
+        ncube = (tau is not None) + (flux is not None)
+        t_loop = d["n_active"] * nch * 1.7e-7                       # ms, measured rate
+        t_fill = (nx - (self._x_hi - self._x_lo)) * nz * nch * ncube * 8 / 3.4e9   # ms, light grid
+        light = 1 if t_loop > t_fill else 0
         for r in range(self._world):
             if r == self._rank:
                 continue
-            lo, hi = sharding.slab_bounds(nx, r, self._world)
+            lo, hi = self._bounds[r]
             ext = meta["extents"][lo * nz: hi * nz]
             st = lib.rjp_fill_missed(ext.data_ptr(), ext.shape[0], nch, nx * nz, lo * nz,
                                      tau.data_ptr() if tau is not None else None,
                                      flux.data_ptr() if flux is not None else None,
-                                     side.cuda_stream)
+                                     light, side.cuda_stream)
             _cabi.check(st, "rjp_fill_missed")
             _launched()
         return side
@@ -1054,7 +1086,7 @@ class JetModel:
 
         views = [c.view(c.shape[0], plane) if c is not None else None for c in (tau, flux)]
         sharding.exchange_ray_columns(views, [0.0, float("nan")], self._ray_meta(), nx, nz,
-                                      self._rank, self._world, ops=Ops)
+                                      self._rank, self._world, ops=Ops, bounds=self._bounds)
         torch.cuda.current_stream(d["device"]).wait_stream(side)
 
     def _device_image(self, t, lead=None):
@@ -1063,7 +1095,8 @@ class JetModel:
             return t.view(lead, self._nx, nz)
         t = t.view(nxs, nz) if lead is None else t.view(lead, nxs, nz)
         if self._world > 1:
-            t = gather_x(t, self._nx, self._rank, self._world, dim=0 if lead is None else 1)
+            t = gather_x(t, self._nx, self._rank, self._world, dim=0 if lead is None else 1,
+                         bounds=self._bounds)
         return t
 
     # ------------------------------------------------------------------ public RT methods

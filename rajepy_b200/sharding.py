@@ -26,13 +26,38 @@ def slab_bounds(nx, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def balanced_bounds(weights, world):
+    """Contiguous x-slabs [(lo, hi)] * world with (nearly) equal summed `weights` (one weight
+    per x-plane, e.g. an estimate of the in-jet cells of the plane): the jet occupies a narrow
+    range of x, so equal-width slabs would leave most ranks without any ray to integrate, and
+    empty space costs nothing in the sparse fill / ray walk.  Every rank gets >= 1 plane."""
+    import numpy as np
+    w = np.asarray(weights, dtype=np.float64)
+    nx = w.size
+    if world < 1 or world > nx:
+        raise ValueError("more ranks than x-planes")
+    w = w + max(w.sum(), 1.0) * 1e-6 / nx          # empty planes still cost a little
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for k in range(1, world):
+        c = int(np.searchsorted(cum, cum[-1] * k / world, side="left"))
+        c = min(max(c, cuts[-1] + 1), nx - (world - k))
+        cuts.append(c)
+    cuts.append(nx)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def even_bounds(nx, world):
+    return [slab_bounds(nx, r, world) for r in range(world)]
+
+
 def epoch_shares(n_epochs, rank, world):
     """Indices of the epochs `rank` integrates when a time series is sharded by epoch
     (BASELINE config 4): round-robin keeps the per-rank cost even."""
     return list(range(rank, n_epochs, world))
 
 
-def gather_x(tile, nx, rank, world, dim=0, group=None):
+def gather_x(tile, nx, rank, world, dim=0, group=None, bounds=None):
     """All-gather x-slab tiles along dimension `dim` into the full array (every rank gets
     the full result).  `tile` is a torch tensor on the device NCCL/gloo is bound to.
 
@@ -46,7 +71,7 @@ def gather_x(tile, nx, rank, world, dim=0, group=None):
         return tile
     if not dist.is_initialized():
         raise RuntimeError("sharded JetModel needs torch.distributed to be initialised")
-    sizes = [hi - lo for lo, hi in (slab_bounds(nx, r, world) for r in range(world))]
+    sizes = [hi - lo for lo, hi in (bounds or even_bounds(nx, world))]
     tile = tile.contiguous()
     big = max(sizes)
     if min(sizes) == big:
@@ -126,14 +151,16 @@ class TorchColumnOps:
                 cube[:, miss] = v
 
 
-def build_ray_meta(extents_tile, ray_list_tile, x_lo, nx, nz, rank, world, group=None):
+def build_ray_meta(extents_tile, ray_list_tile, x_lo, nx, nz, rank, world, group=None,
+                   bounds=None):
     """Exchange, once per model, what the sparse cube gather needs: the per-ray extents of
     every slab and the sorted GLOBAL ids (x * nz + z) of every slab's jet-crossing rays.
     `extents_tile` (nxs*nz, 2) int32, `ray_list_tile` (n_active,) int32 slab-local ids."""
     import torch
     import torch.distributed as dist
     nxs = extents_tile.shape[0] // nz
-    ext = gather_x(extents_tile.view(nxs, nz, 2), nx, rank, world, dim=0, group=group)
+    ext = gather_x(extents_tile.view(nxs, nz, 2), nx, rank, world, dim=0, group=group,
+                   bounds=bounds)
     ext = ext.contiguous().view(nx * nz, 2)
     ids = torch.sort(ray_list_tile.to(torch.int32))[0] + x_lo * nz
     cnt = torch.tensor([ids.numel()], dtype=torch.int64, device=ids.device)
@@ -150,7 +177,7 @@ def build_ray_meta(extents_tile, ray_list_tile, x_lo, nx, nz, rank, world, group
 
 
 def exchange_ray_columns(cubes, values, meta, nx, nz, rank, world, ops=TorchColumnOps,
-                         group=None):
+                         group=None, bounds=None):
     """Complete full-size cubes (nchan, nx*nz) whose rows of the own slab are final: all-gather
     the columns of the jet-crossing rays of every slab and write the constants `values[i]`
     (tau: 0, flux: NaN) of the rays that miss the jet in the other slabs.  Entries of `cubes`
@@ -169,7 +196,7 @@ def exchange_ray_columns(cubes, values, meta, nx, nz, rank, world, ops=TorchColu
     for r in range(world):
         if r == rank:
             continue
-        lo, hi = slab_bounds(nx, r, world)
+        lo, hi = (bounds or even_bounds(nx, world))[r]
         ops.fill_missed(meta["extents"][lo * nz: hi * nz], lo * nz, cubes, values)
         for i, cube in enumerate(live):
             ops.scatter(recv[r, i], meta["ids"][r], cube)

@@ -187,3 +187,34 @@ def test_slab_bounds_cover_grid():
     assert sharding.epoch_shares(64, 3, 8) == list(range(3, 64, 8))
     with pytest.raises(ValueError):
         sharding.slab_bounds(4, 0, 8)
+
+
+def test_balanced_bounds_tile_the_grid_and_balance_work():
+    rng = np.random.default_rng(3)
+    for nx, world in ((50, 8), (1024, 8), (17, 17), (64, 3)):
+        w = np.zeros(nx)
+        c = nx // 2
+        w[max(0, c - nx // 16 - 1): c + nx // 16 + 1] = rng.uniform(1, 5, size=len(
+            w[max(0, c - nx // 16 - 1): c + nx // 16 + 1]))
+        b = sharding.balanced_bounds(w, world)
+        assert b[0][0] == 0 and b[-1][1] == nx
+        assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        assert all(hi > lo for lo, hi in b)
+        if nx >= 8 * world:
+            share = np.array([w[lo:hi].sum() for lo, hi in b])
+            assert share.max() <= w.sum() / world + w.max() + 1e-9
+    z = sharding.balanced_bounds(np.zeros(12), 4)          # no jet at all: near-even split
+    assert z[0][0] == 0 and z[-1][1] == 12 and all(2 <= hi - lo <= 4 for lo, hi in z)
+    with pytest.raises(ValueError):
+        sharding.balanced_bounds(np.ones(3), 4)
+
+
+def test_sharded_models_agree_on_work_balanced_slabs():
+    p = cases.with_grid(cases.base_params(), 64, 64, 64)
+    slabs = [_model(p, shard=(r, 4)).slab for r in range(4)]
+    assert slabs[0][0] == 0 and slabs[-1][1] == 64
+    assert all(slabs[i][1] == slabs[i + 1][0] for i in range(3))
+    widths = [hi - lo for lo, hi in slabs]
+    assert min(widths[1:3]) < min(widths[0], widths[3])      # the jet sits in the middle planes
+    even = [_model(p, shard=(r, 4), balance=False).slab for r in range(4)]
+    assert even == [(0, 16), (16, 32), (32, 48), (48, 64)]

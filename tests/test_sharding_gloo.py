@@ -78,7 +78,7 @@ def test_sharded_model_slabs_are_consistent():
 
 
 # ------------------------------------------------------------------ sparse cube exchange
-def _exchange_worker(rank, world, port, nx, nz, path, out_dir):
+def _exchange_worker(rank, world, port, nx, nz, path, out_dir, bounds):
     import torch
     import torch.distributed as dist
     from rajepy_b200 import sharding
@@ -86,7 +86,7 @@ def _exchange_worker(rank, world, port, nx, nz, path, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     d = np.load(path)
-    lo, hi = sharding.slab_bounds(nx, rank, world)
+    lo, hi = bounds[rank] if bounds else sharding.slab_bounds(nx, rank, world)
     nch = d["tau"].shape[0]
     # what a rank holds after its own pass: full-size cubes whose rows of the OWN slab are
     # final, everything else uninitialised (poisoned here)
@@ -100,25 +100,29 @@ def _exchange_worker(rank, world, port, nx, nz, path, out_dir):
                                                  d["extents"][lo * nz: hi * nz, 1])
                                   .astype(np.int32))
     local_rays = local_rays[torch.randperm(local_rays.numel())]   # the GPU list is unordered
-    meta = sharding.build_ray_meta(ext, local_rays, lo, nx, nz, rank, world)
+    meta = sharding.build_ray_meta(ext, local_rays, lo, nx, nz, rank, world, bounds=bounds)
     assert sum(meta["counts"]) == int((d["extents"][:, 0] < d["extents"][:, 1]).sum())
-    sharding.exchange_ray_columns(cubes, [0.0, float("nan")], meta, nx, nz, rank, world)
+    sharding.exchange_ray_columns(cubes, [0.0, float("nan")], meta, nx, nz, rank, world,
+                                  bounds=bounds)
     # tau only (flux not requested)
     only = torch.from_numpy(np.where(np.arange(nx)[None, :, None] // 1 >= 0, 7.0, 7.0) *
                             np.ones((nch, nx, nz))).view(nch, nx * nz)
     only.view(nch, nx, nz)[:, lo:hi] = torch.from_numpy(d["tau"][:, lo:hi])
-    sharding.exchange_ray_columns([only, None], [0.0, float("nan")], meta, nx, nz, rank, world)
+    sharding.exchange_ray_columns([only, None], [0.0, float("nan")], meta, nx, nz, rank, world,
+                                  bounds=bounds)
     np.savez(os.path.join(out_dir, f"x{rank}.npz"), tau=cubes[0].view(nch, nx, nz).numpy(),
              flux=cubes[1].view(nch, nx, nz).numpy(), only=only.view(nch, nx, nz).numpy())
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_sparse_cube_exchange(world):
+@pytest.mark.parametrize("world,bounds", [(2, None), (4, None),
+                                          (4, [(0, 7), (7, 9), (9, 10), (10, 18)])])
+def test_sparse_cube_exchange(world, bounds):
     """Only the cube columns of jet-crossing rays travel; every rank rebuilds the constants
     of the other slabs from the all-gathered extents.  The result must be the full oracle
-    cube on every rank (18 planes over 4 ranks: uneven slabs)."""
+    cube on every rank (18 planes over 4 ranks: uneven slabs; work-balanced slabs of very
+    different widths, one of them a single plane)."""
     import torch.multiprocessing as mp
     from oracle import rajepy_oracle as orc
     p = cases.with_grid(cases.base_params(), 18, 24, 30)
@@ -136,7 +140,7 @@ def test_sparse_cube_exchange(world):
     tmp = tempfile.mkdtemp()
     path = os.path.join(tmp, "in.npz")
     np.savez(path, tau=tau, flux=flux, extents=extents)
-    mp.spawn(_exchange_worker, args=(world, _free_port(), oj.nx, oj.nz, path, tmp),
+    mp.spawn(_exchange_worker, args=(world, _free_port(), oj.nx, oj.nz, path, tmp, bounds),
              nprocs=world, join=True)
     for r in range(world):
         out = np.load(os.path.join(tmp, f"x{r}.npz"))
