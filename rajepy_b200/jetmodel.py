@@ -48,6 +48,7 @@ def _torch():
 # model) instead of the whole 17 B/cell state.  A buffer that is not in the pool is allocated
 # zero-filled, which is the state an all-zero occupancy map describes.
 _STATE_POOL = {}
+_PLANE_WEIGHTS = {}     # slab-balancing estimate per geometry (host work, ~20 ms once)
 
 
 def _take_state(torch, dev, ncell, nbricks):
@@ -221,7 +222,12 @@ class JetModel:
         slab boundaries without communicating."""
         g = self._params["geometry"]
         nx, ny, nz, cs = self._nx, self._ny, self._nz, self._csize
-        sx, sy, sz = max(1, nx // 256), max(1, ny // 96), max(1, nz // 96)
+        key = (nx, ny, nz, float(cs), float(g["inc"]), float(g["pa"]), float(g["w_0"]),
+               float(g["r_0"]), float(g["mod_r_0"]), float(g["epsilon"]))
+        hit = _PLANE_WEIGHTS.get(key)
+        if hit is not None:
+            return hit
+        sx, sy, sz = max(1, nx // 256), max(1, ny // 64), max(1, nz // 64)
         ix = np.arange(sx // 2, nx, sx)
         iy = np.arange(sy // 2, ny, sy)
         iz = np.arange(sz // 2, nz, sz)
@@ -234,7 +240,11 @@ class JetModel:
             inside = (w <= hm.w_r(r, g["w_0"], g["mod_r_0"], g["r_0"], g["epsilon"])) & \
                      (np.abs(r) >= g["r_0"])
         coarse = inside.sum(axis=(1, 2)).astype(np.float64)
-        return np.interp(np.arange(nx), ix, coarse)
+        out = np.interp(np.arange(nx), ix, coarse)
+        if len(_PLANE_WEIGHTS) > 32:
+            _PLANE_WEIGHTS.clear()
+        _PLANE_WEIGHTS[key] = out
+        return out
 
     # ------------------------------------------------------------------ text table
     def __str__(self):
