@@ -226,9 +226,10 @@ def run_gpu(args):
     nchan_total = len(cont) + len(chans)
     units = ncell * nchan_total
 
-    def make_model():
+    def make_model(host_ranks=None):
         import copy
-        jm = rb.JetModel(copy.deepcopy(params), log=log, device=dev, shard=(rank, world))
+        jm = rb.JetModel(copy.deepcopy(params), log=log, device=dev, shard=(rank, world),
+                         host_ranks=host_ranks)
         jm.time = 1.0 * con.year
         return jm
 
@@ -254,11 +255,15 @@ def run_gpu(args):
 
     def e2e_step():
         """Through the public JetModel API with host (numpy) results."""
-        jm = make_model()
+        # N > 1: the products land on rank 0's host (the rank that writes the FITS files);
+        # the other ranks take part in the exchange only
+        jm = make_model(host_ranks=(0,) if world > 1 else None)
         s_ff = jm.flux_ff(cont)
         t_l = jm.optical_depth_rrl(line, chans)
         s_l = jm.flux_rrl(line, chans, contsub=False)
         jm.release()
+        if s_l is None:
+            return 0, 0.0
         return s_ff.nbytes + t_l.nbytes + s_l.nbytes, float(np.nansum(s_l[len(chans) // 2]))
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -325,8 +330,9 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "note": "JetModel(params) -> flux_ff(16 freqs), optical_depth_rrl, "
-                            "flux_rrl(contsub=False) returned as numpy arrays; inputs are "
-                            "the parameter dict (no bulk H2D exists on this path)",
+                            "flux_rrl(contsub=False) returned as numpy arrays (N > 1: on rank "
+                            "0, host_ranks=(0,)); inputs are the parameter dict (no bulk H2D "
+                            "exists on this path); bound by the device->host copy of the cubes",
                     "checksum_jy": checksum},
             "roofline": {"bound": "hbm",
                          "kernel": "integration pass: integrate_line_kernel (K3+K4+K5 ray walk) "

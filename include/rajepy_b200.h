@@ -224,7 +224,10 @@ int rjp_integrate(const rjp_model* m_host, const rjp_epoch* ep_host,
  *   rjp_scatter_rays cube[c * cube_plane + ray_ids[k]] = in[c * n_stride + k]
  *   rjp_fill_missed  for the nray rays described by `extents` (any slab's, e.g. all-gathered):
  *                    tau = 0 / flux = NaN in every channel plane where the extent is empty;
- *                    ray i is element cube_offset + i of a plane.  tau or flux may be NULL.
+ *                    ray i is element cube_offset + i of a plane; rays in [skip_lo, skip_hi)
+ *                    are left untouched (the caller's own slab when `extents` covers the
+ *                    whole image: ONE launch then writes every other slab's constants).
+ *                    tau or flux may be NULL.
  *                    light != 0: a small grid meant to run on a side stream beside a long
  *                    channel loop; 0: a grid that reaches the HBM write bandwidth alone.
  * ray_ids index into a plane (global ray = x * nz + z for a full-size cube).          */
@@ -233,7 +236,8 @@ int rjp_pack_rays(const double* cube, int64_t cube_plane, const int32_t* ray_ids
 int rjp_scatter_rays(const double* in, int32_t n_stride, const int32_t* ray_ids, int32_t n,
                      int32_t nchan, double* cube, int64_t cube_plane, void* stream);
 int rjp_fill_missed(const int32_t* extents, int64_t nray, int32_t nchan, int64_t cube_plane,
-                    int64_t cube_offset, double* tau, double* flux, int32_t light, void* stream);
+                    int64_t cube_offset, int64_t skip_lo, int64_t skip_hi, double* tau,
+                    double* flux, int32_t light, void* stream);
 
 /* Continuum epilogue (K5) for nfreq frequencies from one pass' kff/tsum/tcount:
  *   tau[f] = cff[f] * kff;  I[f] = iff[f] * Tmean * (1 - exp(-tau));  S[f] = I * omega_jy

@@ -107,7 +107,7 @@ def load():
                                   C.POINTER(Channels), i32, i32, vp, vp, i64, i64, vp, vp]
     lib.rjp_pack_rays.argtypes = [vp, i64, vp, i32, i32, i32, vp, vp]
     lib.rjp_scatter_rays.argtypes = [vp, i32, vp, i32, i32, vp, i64, vp]
-    lib.rjp_fill_missed.argtypes = [vp, i64, i32, i64, i64, vp, vp, i32, vp]
+    lib.rjp_fill_missed.argtypes = [vp, i64, i32, i64, i64, i64, i64, vp, vp, i32, vp]
     lib.rjp_continuum_images.argtypes = [vp, vp, vp, i64, vp, vp, dbl, i32, vp, vp, vp, vp]
     lib.rjp_voigt_profile.argtypes = [vp, vp, i64, vp, vp]
     for f in ("rjp_struct_sizes", "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field",

@@ -18,8 +18,8 @@ int rjp_launch_integrate(const rjp_model*, const rjp_epoch*, const rjp_continuum
                          double*, int32_t*, const rjp_line*, const rjp_channels*, int, int,
                          double, double*, double*, long long, long long, cudaStream_t,
                          cudaStream_t);
-int rjp_launch_fill_missed(const int32_t*, long long, int, long long, long long, double*, double*,
-                           int, cudaStream_t);
+int rjp_launch_fill_missed(const int32_t*, long long, int, long long, long long, long long,
+                           long long, double*, double*, int, cudaStream_t);
 int rjp_launch_pack_rays(const double*, long long, const int32_t*, int, int, int, double*,
                          cudaStream_t);
 int rjp_launch_scatter_rays(const double*, int, const int32_t*, int, int, double*, long long,
@@ -163,13 +163,15 @@ extern "C" int rjp_voigt_profile(const double* x, const double* y, int64_t n, do
 }
 
 extern "C" int rjp_fill_missed(const int32_t* extents, int64_t nray, int32_t nchan,
-                               int64_t cube_plane, int64_t cube_offset, double* tau, double* flux,
-                               int32_t light, void* stream) {
+                               int64_t cube_plane, int64_t cube_offset, int64_t skip_lo,
+                               int64_t skip_hi, double* tau, double* flux, int32_t light,
+                               void* stream) {
   if (nray < 0 || nchan < 0 || (nray > 0 && !extents) || cube_plane < cube_offset + nray ||
-      cube_offset < 0 || (!tau && !flux))
+      cube_offset < 0 || (!tau && !flux) || skip_lo < 0 || skip_hi < skip_lo)
     return RJP_ERR_ARG;
-  return check_launch(rjp_launch_fill_missed(extents, nray, nchan, cube_plane, cube_offset, tau,
-                                             flux, light, (cudaStream_t)stream));
+  return check_launch(rjp_launch_fill_missed(extents, nray, nchan, cube_plane, cube_offset,
+                                             skip_lo, skip_hi, tau, flux, light,
+                                             (cudaStream_t)stream));
 }
 
 extern "C" int rjp_pack_rays(const double* cube, int64_t cube_plane, const int32_t* ray_ids,

@@ -331,11 +331,12 @@ missed_rays_kernel(const int2* __restrict__ extents, size_t nray, int nchan,
                    double* __restrict__ em, double* __restrict__ kff,
                    double* __restrict__ tsum, int32_t* __restrict__ tcount,
                    double* __restrict__ tau, double* __restrict__ flux, size_t plane,
-                   size_t offset) {
+                   size_t offset, size_t skip_lo, size_t skip_hi) {
   // persistent: a warp takes 128 consecutive rays at a time (4 per lane) and loops over the
   // channel planes -- no loads inside the store stream; a light grid leaves the SMs to the
   // channel loop.  Ray i of `extents` is element offset + i of every cube plane (plane =
-  // elements per plane): a slab writes into its rows of a full-size cube this way.
+  // elements per plane): a slab writes into its rows of a full-size cube this way.  Rays in
+  // [skip_lo, skip_hi) are left alone (multi-GPU: the own slab inside the global ray range).
   RJP_STAMP_BEGIN(1)
   const int lane = threadIdx.x & 31;
   const size_t gw = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -348,7 +349,7 @@ missed_rays_kernel(const int2* __restrict__ extents, size_t nray, int nchan,
     for (int k = 0; k < 4; ++k) {
       const size_t ray = r0 + lane + 32 * k;
       miss[k] = false;
-      if (ray < nray) {
+      if (ray < nray && !(ray >= skip_lo && ray < skip_hi)) {
         const int2 e = __ldg(extents + ray);
         miss[k] = e.x >= e.y;
       }
@@ -784,7 +785,7 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
   // every other SM keeps 3.4 TB/s of stores in flight), launched first so that it is
   // resident beside the ray kernels; measured best of 74..1184 CTAs x 32..256 threads
   missed_rays_kernel<<<74, 64, 0, stream>>>(ex2, nray, lines ? nchan : 0, em, kff, tsum, tcount,
-                                            tau_rrl, flux_rrl, plane, coff);
+                                            tau_rrl, flux_rrl, plane, coff, 0, 0);
   if (lines && n_active > 0) {
     // channel blocks of at most 8 * 256 channels per launch; the first one also writes the
     // continuum images of its rays
@@ -836,17 +837,16 @@ extern "C" int rjp_debug_stamps(unsigned long long* out4) {
 #endif
 
 extern "C" int rjp_launch_fill_missed(const int32_t* extents, long long nray, int nchan,
-                                      long long plane, long long offset, double* tau,
-                                      double* flux, int light, cudaStream_t stream) {
+                                      long long plane, long long offset, long long skip_lo,
+                                      long long skip_hi, double* tau, double* flux, int light,
+                                      cudaStream_t stream) {
   if (nray <= 0 || nchan <= 0) return RJP_OK;
   set_carveouts();
   // light grid: meant to run on a side stream beside a long channel loop (multi-GPU: the
   // constants of the OTHER slabs' rays); otherwise a grid that reaches the HBM write peak
   missed_rays_kernel<<<light ? 148 : 148 * 4, light ? 64 : 128, 0, stream>>>(
-      reinterpret_cast<const int2*>(extents),
-                                                  (size_t)nray, nchan, nullptr, nullptr, nullptr,
-                                                  nullptr, tau, flux, (size_t)plane,
-                                                  (size_t)offset);
+      reinterpret_cast<const int2*>(extents), (size_t)nray, nchan, nullptr, nullptr, nullptr,
+      nullptr, tau, flux, (size_t)plane, (size_t)offset, (size_t)skip_lo, (size_t)skip_hi);
   return RJP_OK;
 }
 

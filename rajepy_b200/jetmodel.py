@@ -126,7 +126,8 @@ class JetModel:
             raise err
         return mod.params
 
-    def __init__(self, params, log=None, device=None, shard=None, balance=True):
+    def __init__(self, params, log=None, device=None, shard=None, balance=True,
+                 host_ranks=None):
         if isinstance(params, dict):
             self._params = params
         elif isinstance(params, str):
@@ -203,6 +204,10 @@ class JetModel:
         if shard is None:
             shard = (0, 1)
         self._rank, self._world = int(shard[0]), int(shard[1])
+        # sharded models: ranks that receive the products as host (numpy) arrays; the others
+        # take part in the exchange and get None (e.g. host_ranks=(0,) when only rank 0 writes
+        # the FITS files).  None = every rank, the drop-in behaviour.
+        self._host_ranks = None if host_ranks is None else {int(r) for r in host_ranks}
         # x-slabs of equal estimated work (in-jet cells), not equal width: see _plane_weights
         self._bounds = balanced_bounds(self._plane_weights(), self._world) \
             if (balance and self._world > 1) else even_bounds(self._nx, self._world)
@@ -960,13 +965,15 @@ class JetModel:
     def _host_image(self, t, lead=None):
         """Device tile(s) -> full host numpy array, all-gathering x-slabs if sharded."""
         nxs, nz = self._x_hi - self._x_lo, self._nz
+        wanted = self._host_ranks is None or self._rank in self._host_ranks
         if lead is not None and self._world > 1 and t.numel() == lead * self._nx * nz:
-            return _to_host(t.view(lead, self._nx, nz))      # cube completed by _exchange_cubes
+            # cube completed by _exchange_cubes
+            return _to_host(t.view(lead, self._nx, nz)) if wanted else None
         t = t.view(nxs, nz) if lead is None else t.view(lead, nxs, nz)
         if self._world > 1:
             t = gather_x(t, self._nx, self._rank, self._world, dim=0 if lead is None else 1,
                          bounds=self._bounds)
-        return _to_host(t)
+        return _to_host(t) if wanted else None
 
     def _continuum_images_device(self, freqs, want):
         """K5 for a list of frequencies; `want` in ('tau', 'intensity', 'flux').
@@ -1050,17 +1057,17 @@ class JetModel:
         t_loop = d["n_active"] * nch * 1.7e-7                       # ms, measured rate
         t_fill = (nx - (self._x_hi - self._x_lo)) * nz * nch * ncube * 8 / 3.4e9   # ms, light grid
         light = 1 if t_loop > t_fill else 0
-        for r in range(self._world):
-            if r == self._rank:
-                continue
-            lo, hi = self._bounds[r]
-            ext = meta["extents"][lo * nz: hi * nz]
-            st = lib.rjp_fill_missed(ext.data_ptr(), ext.shape[0], nch, nx * nz, lo * nz,
-                                     tau.data_ptr() if tau is not None else None,
-                                     flux.data_ptr() if flux is not None else None,
-                                     light, side.cuda_stream)
-            _cabi.check(st, "rjp_fill_missed")
-            _launched()
+        # ONE launch for all other slabs (own rays skipped), queued before the channel loop so
+        # that its CTAs are resident beside it: a kernel launched after the loop has filled
+        # the SMs starves until the loop's whole CTA queue has drained
+        ext = meta["extents"]
+        st = lib.rjp_fill_missed(ext.data_ptr(), ext.shape[0], nch, nx * nz, 0,
+                                 self._x_lo * nz, self._x_hi * nz,
+                                 tau.data_ptr() if tau is not None else None,
+                                 flux.data_ptr() if flux is not None else None,
+                                 light, side.cuda_stream)
+        _cabi.check(st, "rjp_fill_missed")
+        _launched()
         return side
 
     def _exchange_cubes(self, tau, flux, side):
@@ -1113,6 +1120,8 @@ class JetModel:
     def emission_measure(self, savefits=False):
         """Emission measure viewed along the y-axis [pc cm^-6] (classes.py:1101-1128)"""
         ems = self._host_image(self._pass()["em"])
+        if ems is None:
+            return None
         if savefits:
             self.save_fits(reorder_axes(ems, ra_axis=0, dec_axis=1), savefits, 'em')
         return ems
@@ -1124,6 +1133,8 @@ class JetModel:
             tff = self._cellwise_tau_ff(np.atleast_1d(freq))
             return tff[0] if scalar else tff
         tff = self._continuum_images(freq, 'tau')
+        if tff is None:
+            return None
         if scalar:
             tff = tff[0]
         if savefits:
@@ -1134,6 +1145,8 @@ class JetModel:
         """Intensity along the y-axis [W m^-2 Hz^-1 sr^-1] (classes.py:1449-1496)"""
         scalar = np.isscalar(freq)
         ints = self._continuum_images(freq, 'intensity')
+        if ints is None:
+            return None
         if scalar:
             ints = ints[0]
         if savefits:
@@ -1144,6 +1157,8 @@ class JetModel:
         """Flux [Jy/pixel] (classes.py:1498-1541)"""
         scalar = np.isscalar(freq)
         fluxes = self._continuum_images(freq, 'flux')
+        if fluxes is None:
+            return None
         if scalar:
             fluxes = fluxes[0]
         if savefits:
@@ -1160,6 +1175,8 @@ class JetModel:
         res = self._pass(rrl, freqs, contsub=self._line_contsub_hint(), want_tau=True,
                          want_flux=True)
         tau = self._host_image(res["tau"], lead=freqs.size)
+        if tau is None:
+            return None
         if scalar:
             tau = tau[0]
         if savefits:
@@ -1178,8 +1195,10 @@ class JetModel:
         scalar = np.isscalar(freq)
         freqs = np.atleast_1d(np.asarray(freq, dtype=np.float64))
         res = self._pass(rrl, freqs, contsub=True, want_tau=True, want_flux=True)
-        ints = self._host_image(res["flux"], lead=freqs.size) * \
-            (1e-26 / self._pixel_solid_angle())
+        ints = self._host_image(res["flux"], lead=freqs.size)
+        if ints is None:
+            return None
+        ints = ints * (1e-26 / self._pixel_solid_angle())
         if scalar:
             ints = ints[0]
         if savefits:
@@ -1194,6 +1213,8 @@ class JetModel:
         freqs = np.atleast_1d(np.asarray(freq, dtype=np.float64))
         res = self._pass(rrl, freqs, contsub=contsub, want_tau=True, want_flux=True)
         fluxes = self._host_image(res["flux"], lead=freqs.size)
+        if fluxes is None:
+            return None
         if scalar:
             fluxes = fluxes[0]
         if savefits:

@@ -49,6 +49,21 @@ def _worker(rank, world, port, out_dir):
     ok = all(np.array_equal(np.nan_to_num(a), np.nan_to_num(b)) and
              np.array_equal(np.isnan(a), np.isnan(b))
              for a, b in zip(res["one"], res["sharded"]))
+    # products on rank 0's host only: the other ranks take part in the exchange and get None
+    jm = rb.JetModel(cases.with_grid(cases.base_params(), 64, 96, 128), log=log,
+                     device=f"cuda:{rank}", shard=(rank, world), host_ranks=(0,))
+    jm.time = 0.9 * con.year
+    em, cube = jm.emission_measure(), jm.flux_rrl('H58a', chans, contsub=False)
+    if rank == 0:
+        ok = ok and np.array_equal(em, res["one"][1]) and \
+            np.array_equal(np.nan_to_num(cube), np.nan_to_num(res["one"][4]))
+    else:
+        ok = ok and em is None and cube is None
+    # equal-width slabs give the same products as the work-balanced ones
+    jm = rb.JetModel(cases.with_grid(cases.base_params(), 64, 96, 128), log=log,
+                     device=f"cuda:{rank}", shard=(rank, world), balance=False)
+    jm.time = 0.9 * con.year
+    ok = ok and np.array_equal(jm.optical_depth_rrl('H58a', chans), res["one"][3])
     open(os.path.join(out_dir, f"r{rank}.txt"), "w").write("ok" if ok else "MISMATCH")
     dist.barrier()
     dist.destroy_process_group()

@@ -39,9 +39,14 @@ def main():
     orig_fill, orig_exch = jm._fill_remote_constants, jm._exchange_cubes
     orig_pack = sharding.exchange_ray_columns
 
+    side_marks = []
+
     def fill(*a):
         mark("start")
         r = orig_fill(*a)
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(r)                      # end of the remote constant fills on the side stream
+        side_marks.append(e)
         return r
 
     def exch(tau, flux, side):
@@ -52,6 +57,7 @@ def main():
     jm._fill_remote_constants, jm._exchange_cubes = fill, exch
     for it in range(4):
         marks.clear()
+        side_marks.clear()
         jm._line = None
         dist.barrier()
         torch.cuda.synchronize()
@@ -60,6 +66,7 @@ def main():
     t0 = marks[0][1]
     txt = f"rank {rank}: n_active={jm._dev['n_active']} " + ", ".join(
         f"{n} @ {t0.elapsed_time(e):.2f} ms" for n, e in marks)
+    txt += f", side stream fills done @ {t0.elapsed_time(side_marks[0]):.2f} ms, slab {jm.slab}"
     print(txt, file=sys.stderr, flush=True)
     # exchange alone
     tau, flux = jm._line["tau"], jm._line["flux"]
