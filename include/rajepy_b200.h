@@ -248,6 +248,16 @@ int rjp_continuum_images(const double* kff, const double* tsum, const int32_t* t
                          double omega_jy, int32_t nfreq, double* tau, double* intensity,
                          double* flux, void* stream);
 
+/* Line-of-sight means of the cell properties for the model plot (replaces the four
+ * np.nanmean(<3-D grid>, axis=los) of plotting/functions.py:539-590 and the nanmin / nanmax
+ * that scale its colour bars), from the ray walk: out is [7][nxs*nz] double =
+ *   0 mean number density (with the burst factor, classes.py:872-899)   1 mean temperature
+ *   2 mean ionisation fraction   3 mean (v_los - v_lsr) [km/s]
+ *   4 min n, 5 max n, 6 max T along the ray;   NaN where the ray has no finite value.     */
+int rjp_los_means(const rjp_model* m_host, const rjp_epoch* ep_host, const uint8_t* nverts,
+                  const int32_t* extents, const int32_t* ray_list, int32_t n_active,
+                  double* out, void* stream);
+
 /* Voigt profile function of the channel loop, element-wise: out[i] = Re w(x[i] + i y[i]),
  * w = Faddeeva function, y > 0, evaluated by the same device routines the line-of-sight pass
  * uses (mixed fp64/fp32 split for RJP_VT_Y_MIN <= y <= 0.1, fp64 rational approximation

@@ -29,6 +29,8 @@ int rjp_launch_continuum_images(const double*, const double*, const int32_t*, in
                                 const double*, const double*, double, int, double*, double*,
                                 double*, cudaStream_t);
 int rjp_launch_voigt_profile(const double*, const double*, int64_t, double*, cudaStream_t);
+int rjp_launch_los_means(const rjp_model*, const rjp_epoch*, const uint8_t*, const int32_t*,
+                         const int32_t*, int, double*, cudaStream_t);
 }
 
 static thread_local char g_cuda_err[256] = "";
@@ -190,4 +192,17 @@ extern "C" int rjp_scatter_rays(const double* in, int32_t n_stride, const int32_
     return RJP_ERR_ARG;
   return check_launch(rjp_launch_scatter_rays(in, n_stride, ray_ids, n, nchan, cube, cube_plane,
                                               (cudaStream_t)stream));
+}
+
+extern "C" int rjp_los_means(const rjp_model* m, const rjp_epoch* ep, const uint8_t* nverts,
+                             const int32_t* extents, const int32_t* ray_list, int32_t n_active,
+                             double* out, void* stream) {
+  if (!model_ok(m) || !ep || !nverts || !extents || !out || n_active < 0 ||
+      (n_active > 0 && !ray_list))
+    return RJP_ERR_ARG;
+  if (ep->n_blue < 0 || ep->n_blue > RJP_MAX_BURSTS || ep->n_red < 0 ||
+      ep->n_red > RJP_MAX_BURSTS)
+    return RJP_ERR_ARG;
+  return check_launch(rjp_launch_los_means(m, ep, nverts, extents, ray_list, n_active, out,
+                                           (cudaStream_t)stream));
 }

@@ -43,9 +43,8 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 constexpr int ZT = 32;          // rays per CTA of the dense sweep
 constexpr int RPW = 8;          // rows in flight per warp
-#ifndef RJP_VARIANT
-#define RJP_VARIANT 0
-#endif
+// tuning knobs of the channel loop (measured on B200, profiles/README.md: 8 channels per
+// thread and 8 CTAs of 64 threads per SM beat 4 channels / 96-register variants)
 #ifndef RJP_GCH
 #define RJP_GCH 8
 #endif
@@ -308,13 +307,6 @@ __device__ __noinline__ FastEntry to_fast(const LineEntry& s) {
   e.b1 = (float)(s.a1 / s.p0);
   e.b2 = (float)(s.a2 / s.p0);
   return e;
-}
-
-__device__ __noinline__ float vt_core_call(double yy, float y2f, float yf, float ya, uint32_t tab,
-                                           double X, double X2) {
-  FastEntry e;
-  e.yy = yy; e.y2f = y2f; e.yf = yf; e.ya = ya;
-  return vt_core(e, tab, X, X2);
 }
 
 // 1 - exp(-h nu / kT) for nu = nu0 + dn from the cell's value at nu0 (rrls.py:387)
@@ -671,6 +663,70 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   RJP_STAMP_END(0)
 }
 
+// Line-of-sight means of the per-cell properties (what the reference's model plot shows,
+// plotting/functions.py:539-590: np.nanmean(field, axis=los) of number density, temperature,
+// ionisation fraction and v_los - v_lsr) straight from the ray walk, so that the plot does not
+// need four full 3-D grids on the host.  One warp per jet-crossing ray; out[q][ray] for
+// q = 0..6: mean n, mean T, mean x, mean (v_los - v_lsr), min n, max n, max T; NaN where a
+// ray has no finite value (and on every ray that misses the jet: prefilled by the caller).
+__global__ void __launch_bounds__(256)
+los_means_kernel(const rjp_model m, const rjp_epoch ep, const uint8_t* __restrict__ nverts,
+                 const int2* __restrict__ extents, const int32_t* __restrict__ ray_list,
+                 const int n_active, const size_t nray, double* __restrict__ out) {
+  __shared__ Params s_p;
+  stage_params(&s_p, m, ep);
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n_active) return;
+  const int ray = ray_list[w];
+  const int xl = ray / m.nz, iz = ray - xl * m.nz;
+  const int ix = m.x_lo + xl;
+  const int2 ext = extents[ray];
+  const uint8_t* col = nverts + (size_t)xl * m.ny * m.nz + iz;
+  double sum[4] = {0.0, 0.0, 0.0, 0.0};
+  int cnt[4] = {0, 0, 0, 0};
+  double nmin = CUDART_INF, nmax = -CUDART_INF, tmax = -CUDART_INF;
+  for (int iy = ext.x + lane; iy < ext.y; iy += 32) {
+    if (col[(size_t)iy * m.nz] == 0) continue;
+    const Rw g = centroid_rw(s_p.m, ix, iy, iz);
+    const Laws l = laws_of(s_p.m, g, false);
+    const double tl = s_p.ep.time - travel_time(s_p.m, g);
+    const double chi = (g.r < 0.0) ? burst_chi(s_p.ep.red, s_p.ep.n_red, tl)
+                                   : burst_chi(s_p.ep.blue, s_p.ep.n_blue, tl);
+    const double v[4] = {l.nd * chi, l.temp, l.xi, velocity_of(s_p.m, g).vlos_rel};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (v[q] == v[q]) {
+        sum[q] += v[q];
+        cnt[q] += 1;
+      }
+    }
+    if (v[0] == v[0]) {
+      nmin = fmin(nmin, v[0]);
+      nmax = fmax(nmax, v[0]);
+    }
+    if (v[1] == v[1]) tmax = fmax(tmax, v[1]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      sum[q] += __shfl_xor_sync(0xffffffffu, sum[q], o);
+      cnt[q] += __shfl_xor_sync(0xffffffffu, cnt[q], o);
+    }
+    nmin = fmin(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
+    nmax = fmax(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+    tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) out[q * nray + ray] = cnt[q] > 0 ? sum[q] / cnt[q] : dnan();
+    out[4 * nray + ray] = cnt[0] > 0 ? nmin : dnan();
+    out[5 * nray + ray] = cnt[0] > 0 ? nmax : dnan();
+    out[6 * nray + ray] = cnt[1] > 0 ? tmax : dnan();
+  }
+}
+
 // Diagnostic: Re w(x + iy) with the channel loop's own device routines
 __global__ void voigt_profile_kernel(const double* __restrict__ x, const double* __restrict__ y,
                                      int64_t n, double* __restrict__ out) {
@@ -865,6 +921,18 @@ extern "C" int rjp_launch_scatter_rays(const double* in, int n_stride, const int
   if (n <= 0 || nchan <= 0) return RJP_OK;
   scatter_rays_kernel<<<148 * 8, 256, 0, stream>>>(in, n_stride, ray_ids, n, nchan, cube,
                                                    (size_t)plane);
+  return RJP_OK;
+}
+
+extern "C" int rjp_launch_los_means(const rjp_model* m, const rjp_epoch* ep, const uint8_t* nverts,
+                                    const int32_t* extents, const int32_t* ray_list,
+                                    int n_active, double* out, cudaStream_t stream) {
+  const size_t nray = (size_t)(m->x_hi - m->x_lo) * m->nz;
+  // NaN everywhere (all-ones bytes are a quiet NaN), then the jet-crossing rays
+  cudaMemsetAsync(out, 0xFF, sizeof(double) * 7 * nray, stream);
+  if (n_active > 0)
+    los_means_kernel<<<(n_active + 7) / 8, 256, 0, stream>>>(
+        *m, *ep, nverts, reinterpret_cast<const int2*>(extents), ray_list, n_active, nray, out);
   return RJP_OK;
 }
 

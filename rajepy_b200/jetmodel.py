@@ -1005,6 +1005,36 @@ class JetModel:
         out = self._continuum_images_device(freqs, want)
         return self._host_image(out, lead=out.shape[0])
 
+    def los_means(self):
+        """Line-of-sight means of the cell properties, what the reference's model plot draws
+        (plotting/functions.py:539-590) -- without materialising any 3-D grid:
+        {'number_density', 'temperature', 'ion_fraction', 'v_los'} -> (nx, nz) arrays equal to
+        np.nanmean(<property>, axis=1) (v_los relative to v_lsr, km/s), plus the scalars
+        'n_min', 'n_max', 't_max' = nanmin / nanmax over the whole grid."""
+        torch = _torch()
+        lib = _cabi.load()
+        d = self._ensure_filled()
+        dev = d["device"]
+        npix = (self._x_hi - self._x_lo) * self._nz
+        with torch.cuda.device(dev):
+            out = torch.empty((7, npix), dtype=torch.float64, device=dev)
+            st = lib.rjp_los_means(d["model"], self._epoch_struct(), d["nverts"].data_ptr(),
+                                   d["extents"].data_ptr(), d["rays"].data_ptr(),
+                                   d["n_active"], out.data_ptr(), self._stream())
+            _cabi.check(st, "rjp_los_means")
+            _launched()
+        maps = self._host_image(out, lead=7)
+        if maps is None:
+            return None
+        with np.errstate(all="ignore"):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                return {"number_density": maps[0], "temperature": maps[1],
+                        "ion_fraction": maps[2], "v_los": maps[3],
+                        "n_min": float(np.nanmin(maps[4])), "n_max": float(np.nanmax(maps[5])),
+                        "t_max": float(np.nanmax(maps[6]))}
+
     def rt_products(self, cont_freqs=None, line=None, chan_freqs=None, contsub=False,
                     host=True):
         """Batched driver for one epoch (what Pipeline.execute asks of the model per run,
