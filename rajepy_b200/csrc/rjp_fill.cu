@@ -20,7 +20,13 @@
 namespace rjp {
 
 constexpr int TX = 4, TY = 8, TZ = 32;
-constexpr int SBX = 8, SBY = 4;            // bricks per super-brick along x and y
+#ifndef RJP_SBX
+#define RJP_SBX 8
+#endif
+#ifndef RJP_SBY
+#define RJP_SBY 4
+#endif
+constexpr int SBX = RJP_SBX, SBY = RJP_SBY;  // bricks per super-brick along x and y
 constexpr int FILL_THREADS = 256;
 constexpr int NVERT = (TX + 1) * (TY + 1) * (TZ + 1);
 

@@ -49,6 +49,7 @@ def _torch():
 # zero-filled, which is the state an all-zero occupancy map describes.
 _STATE_POOL = {}
 _PLANE_WEIGHTS = {}     # slab-balancing estimate per geometry (host work, ~20 ms once)
+_LINE_STRUCTS = {}      # line constants + per-channel device arrays
 
 
 def _take_state(torch, dev, ncell, nbricks):
@@ -929,10 +930,20 @@ class JetModel:
         return self._line
 
     def _line_structs(self, line, freqs, dev):
-        """Host scalars of the LTE line opacity (classes.py:1159-1169; rrls.py)."""
+        """Host scalars of the LTE line opacity (classes.py:1159-1169; rrls.py) and the
+        per-channel device arrays.  Cached per (line, channels, model constants, device): the
+        Gaunt-factor fits and the host->device copy would otherwise sit between the kernel
+        launches of every pass."""
         torch = _torch()
-        element, n, dn = hm.rrl_parser(line)
         freqs = np.asarray(freqs, dtype=np.float64)
+        key = (line, freqs.tobytes(), str(dev), float(self._csize),
+               float(self._params["target"]["dist"]),
+               float(self._params['properties']['T_0']),
+               float(self._params['power_laws']['q_T']))
+        hit = _LINE_STRUCTS.get(key)
+        if hit is not None:
+            return hit
+        element, n, dn = hm.rrl_parser(line)
         nu0 = hm.rrl_nu_0(element, n, dn)
         m_atom = hm.atomic_mass(element)
         ln = _cabi.Line()
@@ -960,6 +971,9 @@ class JetModel:
         base, step = devarr.data_ptr(), freqs.size * 8
         ch.dnu, ch.nu, ch.cff, ch.aff, ch.bnu = (base, base + step, base + 2 * step,
                                                  base + 3 * step, base + 4 * step)
+        if len(_LINE_STRUCTS) > 16:
+            _LINE_STRUCTS.clear()
+        _LINE_STRUCTS[key] = (ln, ch, devarr)
         return ln, ch, devarr
 
     def _host_image(self, t, lead=None):
