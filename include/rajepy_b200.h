@@ -112,6 +112,8 @@ typedef struct {
   double en_over_k;     /* Z^2 E_n / k_cgs  [K]  (rrls.py:386)                    */
   double h_over_k;      /* h / k [K s]                                            */
   double dn_max;        /* max_k |nu_k - nu0| [Hz] over the channels of this call  */
+  double chan_dnu0;     /* equally spaced channels: dnu[k] = chan_dnu0 + k * chan_step     */
+  double chan_step;     /* [Hz]; 0 = not equally spaced (the kernels then read dnu[])      */
 } rjp_line;
 
 /* Per-channel host-prepared scalars, each a DEVICE array of nchan doubles. */

@@ -51,6 +51,9 @@ constexpr int RPW = 8;          // rows in flight per warp
 #ifndef RJP_MINB64
 #define RJP_MINB64 8
 #endif
+#ifndef RJP_MINB64U
+#define RJP_MINB64U 8
+#endif
 #ifndef RJP_MINB128
 #define RJP_MINB128 4
 #endif
@@ -450,11 +453,14 @@ __global__ void ray_list_kernel(const int2* __restrict__ extents, int nray,
   if (on) list[base + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
-template <int MAXT, int MINB>
+// UNI: the channels are equally spaced (rjp_line.chan_step != 0): the channel offsets are
+// formed on the fly from two per-thread scalars instead of living in 24 registers (16 of
+// which spilled), which is what lets the kernel fit more warps per SM.
+template <int MAXT, int MINB, bool UNI>
 __global__ void __launch_bounds__(MAXT, MINB)
 integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
                       const rjp_line ln, const rjp_channels ch, const int nchan,
-                      const int contsub, const double dn_max,
+                      const int c_first, const int contsub, const double dn_max,
                       const double2* __restrict__ cells, const int2* __restrict__ extents,
                       const int32_t* __restrict__ ray_list, double* __restrict__ em,
                       double* __restrict__ kff, double* __restrict__ tsum,
@@ -489,14 +495,22 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   // thread g owns channels g, g + NT, g + 2 NT, ...: at every step the lanes of a warp hold
   // 32 neighbouring channels, i.e. nearly the same point of the line profile, so the
   // core / wing branches below are (almost always) warp-uniform
-  double dn[GCH];
-  f32x2 dnf2[GCH / 2];
   static_assert(GCH % 2 == 0, "channels are processed in pairs");
+  // channel offsets nu_k - nu0 of this thread's channels g + j NT
+  double dn[UNI ? 1 : GCH];
+  f32x2 dnf2[UNI ? 1 : GCH / 2];
+  const double dstep = ln.chan_step * (double)NT;        // UNI: dn_j = dn[0] + j dstep
+  const float dstepf = (float)dstep;
+  if constexpr (UNI) {
+    dn[0] = ln.chan_dnu0 + (double)(c_first + g) * ln.chan_step;
+    dnf2[0] = pk2((float)dn[0], (float)dn[0]);
+  } else {
 #pragma unroll
-  for (int j = 0; j < GCH; ++j)
-    dn[j] = (g + j * NT < nchan) ? __ldg(ch.dnu + g + j * NT) : 0.0;
+    for (int j = 0; j < GCH; ++j)
+      dn[j] = (g + j * NT < nchan) ? __ldg(ch.dnu + g + j * NT) : 0.0;
 #pragma unroll
-  for (int j = 0; j < GCH; j += 2) dnf2[j >> 1] = pk2((float)dn[j], (float)dn[j + 1]);
+    for (int j = 0; j < GCH; j += 2) dnf2[j >> 1] = pk2((float)dn[j], (float)dn[j + 1]);
+  }
   double acc[GCH];
 #pragma unroll
   for (int j = 0; j < GCH; ++j) acc[j] = 0.0;
@@ -557,10 +571,18 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
       const FastEntry fe = s_fast[i];
       const WingCoef2 wc = vt_wing_coef2(fe);
       const f32x2 b1 = pk2(fe.b1, fe.b1), b2 = pk2(fe.b2, fe.b2);
+      const double X0 = fma(dn[0], fe.inv, fe.xs), dX = dstep * fe.inv;   // UNI only
 #pragma unroll
       for (int j = 0; j < GCH; j += 2) {
         // two channels per step: the fp32 work runs as packed FFMA2
-        const double Xa = fma(dn[j], fe.inv, fe.xs), Xb = fma(dn[j + 1], fe.inv, fe.xs);
+        double Xa, Xb;
+        if constexpr (UNI) {
+          Xa = fma((double)j, dX, X0);
+          Xb = fma((double)(j + 1), dX, X0);
+        } else {
+          Xa = fma(dn[j], fe.inv, fe.xs);
+          Xb = fma(dn[j + 1], fe.inv, fe.xs);
+        }
         const double X2a = Xa * Xa, X2b = Xb * Xb;
         const bool corea = __double2hiint(X2a) < fe.xc2_hi, coreb = __double2hiint(X2b) < fe.xc2_hi;
         const double ra = rcp_seed(X2a), rb = rcp_seed(X2b);
@@ -580,7 +602,11 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
           }
           k2 = pk2(ka, kb);
         }
-        const f32x2 d2 = dnf2[j >> 1];
+        f32x2 d2;
+        if constexpr (UNI)
+          d2 = fma2(pk2((float)j, (float)(j + 1)), pk2(dstepf, dstepf), dnf2[0]);
+        else
+          d2 = dnf2[j >> 1];
         const f32x2 eps = mul2(d2, fma2(d2, b2, b1));
         float ka, kb;
         upk2(fma2(k2, eps, k2), ka, kb);
@@ -595,7 +621,7 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
 #pragma unroll 1
       for (int j = 0; j < GCH; ++j) {
         if (g + j * NT >= nchan) break;
-        const double dnj = dn[j];
+        const double dnj = UNI ? fma((double)j, dstep, dn[0]) : dn[j];
         double sum = 0.0;
         for (int i = 0; i < ns; i += 4) {
           const LineEntry* eb = s_slow + i;
@@ -785,15 +811,16 @@ extern "C" int rjp_launch_ray_list(const int32_t* extents, int nray, int32_t* li
 static void set_carveouts() {
   static bool done = false;
   if (done) return;
-  const int pct = 50;
+  const int pct = 75;
   cudaFuncSetAttribute(missed_rays_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   cudaFuncSetAttribute(continuum_rays_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-  cudaFuncSetAttribute(integrate_line_kernel<64, RJP_MINB64>,
-                       cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-  cudaFuncSetAttribute(integrate_line_kernel<128, RJP_MINB128>,
-                       cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-  cudaFuncSetAttribute(integrate_line_kernel<LINE_THREADS, 2>,
-                       cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  const auto attr = cudaFuncAttributePreferredSharedMemoryCarveout;
+  cudaFuncSetAttribute(integrate_line_kernel<64, RJP_MINB64U, true>, attr, pct);
+  cudaFuncSetAttribute(integrate_line_kernel<128, RJP_MINB128, true>, attr, pct);
+  cudaFuncSetAttribute(integrate_line_kernel<LINE_THREADS, 2, true>, attr, pct);
+  cudaFuncSetAttribute(integrate_line_kernel<64, RJP_MINB64, false>, attr, pct);
+  cudaFuncSetAttribute(integrate_line_kernel<128, RJP_MINB128, false>, attr, pct);
+  cudaFuncSetAttribute(integrate_line_kernel<LINE_THREADS, 2, false>, attr, pct);
   done = true;
 }
 
@@ -855,19 +882,23 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
       double* t_out = tau_rrl ? tau_rrl + off : nullptr;
       double* f_out = flux_rrl ? flux_rrl + off : nullptr;
       double* em_o = (c0 == 0) ? em : nullptr;
-      // 128 registers per thread at every block size (8 CTAs of 64 threads per SM)
-      if (threads <= 64)
-        integrate_line_kernel<64, RJP_MINB64><<<(unsigned)n_active, threads, 0, ls>>>(
-            *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, em_o, kff, tsum, tcount,
-            t_out, f_out, plane, coff);
-      else if (threads <= 128)
-        integrate_line_kernel<128, RJP_MINB128><<<(unsigned)n_active, threads, 0, ls>>>(
-            *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, em_o, kff, tsum, tcount,
-            t_out, f_out, plane, coff);
-      else
-        integrate_line_kernel<LINE_THREADS, 2><<<(unsigned)n_active, threads, 0, ls>>>(
-            *m, *ep, *ct, *ln, cb, nc, contsub, dn_max, c4, ex2, ray_list, em_o, kff, tsum, tcount,
-            t_out, f_out, plane, coff);
+      // equally spaced channels (the normal case) take the register-lean instantiation
+      const bool uni = ln->chan_step != 0.0;
+#define RJP_LAUNCH_LINE(T, B, U)                                                              \
+  integrate_line_kernel<T, B, U><<<(unsigned)n_active, threads, 0, ls>>>(                     \
+      *m, *ep, *ct, *ln, cb, nc, c0, contsub, dn_max, c4, ex2, ray_list, em_o, kff, tsum, tcount, \
+      t_out, f_out, plane, coff)
+      if (threads <= 64) {
+        if (uni) RJP_LAUNCH_LINE(64, RJP_MINB64U, true);
+        else RJP_LAUNCH_LINE(64, RJP_MINB64, false);
+      } else if (threads <= 128) {
+        if (uni) RJP_LAUNCH_LINE(128, RJP_MINB128, true);
+        else RJP_LAUNCH_LINE(128, RJP_MINB128, false);
+      } else {
+        if (uni) RJP_LAUNCH_LINE(LINE_THREADS, 2, true);
+        else RJP_LAUNCH_LINE(LINE_THREADS, 2, false);
+      }
+#undef RJP_LAUNCH_LINE
     }
   } else if (n_active > 0) {
     continuum_rays_kernel<<<(n_active + 7) / 8, 256, 0, ls>>>(*m, *ep, *ct, c4, ex2, ray_list,

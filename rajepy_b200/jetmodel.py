@@ -958,6 +958,14 @@ class JetModel:
         ln.en_over_k = float(z ** 2. * hm.energy_n(n, element) / hm.k_cgs)
         ln.h_over_k = float(hm.h_cgs / hm.k_cgs)
         ln.dn_max = float(np.max(np.abs(freqs - nu0))) if freqs.size else 0.0
+        # equally spaced channels (ContinuumRun.chan_freqs, classes.py:1893-1900): the kernels
+        # form the offsets on the fly instead of reading them
+        ln.chan_dnu0, ln.chan_step = float(freqs[0] - nu0) if freqs.size else 0.0, 0.0
+        if freqs.size > 1:
+            step = (freqs[-1] - freqs[0]) / (freqs.size - 1)
+            dev_max = np.max(np.abs(freqs - (freqs[0] + step * np.arange(freqs.size))))
+            if step != 0.0 and dev_max <= 1e-9 * abs(step):
+                ln.chan_step = float(step)
         omega_jy = self._pixel_solid_angle() / 1e-26
         host = np.stack([
             freqs - nu0,
