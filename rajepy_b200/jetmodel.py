@@ -50,6 +50,8 @@ def _torch():
 _STATE_POOL = {}
 _PLANE_WEIGHTS = {}     # slab-balancing estimate per geometry (host work, ~20 ms once)
 _LINE_STRUCTS = {}      # line constants + per-channel device arrays
+_TIE_DECISIONS = {}     # host re-decisions of near-tie vertices per (geometry, slab, ties)
+_CONT_COEFFS = {}       # per-frequency continuum coefficients on the device
 
 
 def _take_state(torch, dev, ncell, nbricks):
@@ -624,17 +626,11 @@ class JetModel:
         d["rays"] = torch.sort(rays[:max(d["n_active"], 1)])[0].contiguous()
         d["ray_meta"] = None
 
-    def _resolve_ties(self, ties):
-        """Vertices whose inside test the device could not call: decide every
-        (cell, corner) that touches them exactly as classes.py:658-666 does -- corner
-        coordinate cs*(i - n//2) + {0|cs}, maths/geometry.py:181-209 and :96-118 in numpy
-        -- and patch the cells whose count changes."""
-        torch = _torch()
-        lib = _cabi.load()
-        d = self._dev
+    def _decide_ties(self, I, J, K, dec):
+        """{flat slab cell index: change of its vertex count} from the reference's own numpy
+        expression (classes.py:658-666) for every (cell, corner) touching a near-tie vertex."""
         g = self._params["geometry"]
         cs = self._csize
-        I, J, K, dec = ties[:, 0], ties[:, 1], ties[:, 2], ties[:, 3]
         ny, nz = self._ny, self._nz
         delta = {}
         for a in (0, 1):
@@ -657,7 +653,32 @@ class JetModel:
                     flat = ((ii - self._x_lo) * ny + jj) * nz + kk
                     for f, df in zip(flat[diff != 0], diff[diff != 0]):
                         delta[int(f)] = delta.get(int(f), 0) + int(df)
-        delta = {f: v for f, v in delta.items() if v != 0}
+        return {f: v for f, v in delta.items() if v != 0}
+
+    def _resolve_ties(self, ties):
+        """Vertices whose inside test the device could not call: decide every
+        (cell, corner) that touches them exactly as classes.py:658-666 does -- corner
+        coordinate cs*(i - n//2) + {0|cs}, maths/geometry.py:181-209 and :96-118 in numpy
+        -- and patch the cells whose count changes."""
+        torch = _torch()
+        lib = _cabi.load()
+        d = self._dev
+        g = self._params["geometry"]
+        cs = self._csize
+        I, J, K, dec = ties[:, 0], ties[:, 1], ties[:, 2], ties[:, 3]
+        ny, nz = self._ny, self._nz
+        # the decisions are a pure function of the geometry, the slab and the reported ties:
+        # models built from the same parameters (time series, repeated runs) reuse them
+        order = np.lexsort((K, J, I))
+        key = (self._nx, ny, nz, float(cs), self._x_lo, self._x_hi, float(g["inc"]),
+               float(g["pa"]), float(g["w_0"]), float(g["r_0"]), float(g["mod_r_0"]),
+               float(g["epsilon"]), ties[order].tobytes())
+        delta = _TIE_DECISIONS.get(key)
+        if delta is None:
+            delta = self._decide_ties(I, J, K, dec)
+            if len(_TIE_DECISIONS) > 64:
+                _TIE_DECISIONS.clear()
+            _TIE_DECISIONS[key] = delta
         d["n_patched"] = len(delta)
         if not delta:
             return
@@ -1007,8 +1028,15 @@ class JetModel:
         freqs = np.atleast_1d(np.asarray(freqs, dtype=np.float64))
         nf = freqs.size
         npix = c["em"].numel()
-        coeff = torch.from_numpy(np.stack([self._ff_coeff(freqs),
-                                           2. * freqs ** 2. * con.k / con.c ** 2.])).to(dev)
+        ckey = (freqs.tobytes(), str(dev), float(self._params['properties']['T_0']),
+                float(self._params['power_laws']['q_T']))
+        coeff = _CONT_COEFFS.get(ckey)
+        if coeff is None:
+            coeff = torch.from_numpy(np.stack([self._ff_coeff(freqs),
+                                               2. * freqs ** 2. * con.k / con.c ** 2.])).to(dev)
+            if len(_CONT_COEFFS) > 64:
+                _CONT_COEFFS.clear()
+            _CONT_COEFFS[ckey] = coeff
         with torch.cuda.device(dev):
             out = torch.empty((nf, npix), dtype=torch.float64, device=dev)
             ptrs = {k: (out.data_ptr() if k == want else None)
