@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RJP_ABI_VERSION 3
+#define RJP_ABI_VERSION 4
 #define RJP_MAX_BURSTS 16
 
 enum {
@@ -151,10 +151,14 @@ int rjp_struct_sizes(int32_t* model, int32_t* epoch, int32_t* continuum, int32_t
  *                          non-zero = it holds data.  The fill skips bricks that lie outside
  *                          the jet and are already zero, zeroes bricks that lie outside but
  *                          hold data, and updates the map -- so on a zero-initialised or
- *                          recycled buffer it writes only the bricks around the jet.        */
+ *                          recycled buffer it writes only the bricks around the jet.
+ *   brick_work  [rjp_brick_count() + 4] int32 scratch, optional (needs brick_state): enables
+ *                          the two-level sparse fill -- bricks are classified by one thread
+ *                          each into this work list and a persistent grid pulls the bricks
+ *                          that need work one at a time (even load over the SMs).           */
 int rjp_fill_grid(const rjp_model* m_host, uint8_t* nverts, rjp_cell* cells,
-                  uint8_t* brick_state, int32_t* ties, int32_t tie_capacity,
-                  int32_t* n_ties, int32_t* extents, void* stream);
+                  uint8_t* brick_state, int32_t* brick_work, int32_t* ties,
+                  int32_t tie_capacity, int32_t* n_ties, int32_t* extents, void* stream);
 
 /* Number of bricks (entries of brick_state) of the slab described by m_host; < 0 = error. */
 int64_t rjp_brick_count(const rjp_model* m_host);

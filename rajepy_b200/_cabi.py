@@ -97,7 +97,7 @@ def load():
     lib.rjp_abi_version.restype = C.c_int
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     lib.rjp_struct_sizes.argtypes = [C.POINTER(i32)] * 6
-    lib.rjp_fill_grid.argtypes = [C.POINTER(Model), vp, vp, vp, vp, i32, vp, vp, vp]
+    lib.rjp_fill_grid.argtypes = [C.POINTER(Model), vp, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.rjp_patch_cells.argtypes = [C.POINTER(Model), vp, vp, i32, vp, vp, vp, vp, vp]
     lib.rjp_los_means.argtypes = [C.POINTER(Model), C.POINTER(Epoch), vp, vp, vp, i32, vp, vp]
     lib.rjp_los_means.restype = C.c_int

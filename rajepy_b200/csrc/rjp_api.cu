@@ -6,7 +6,7 @@
 #include "../../include/rajepy_b200.h"
 
 extern "C" {
-int rjp_launch_fill(const rjp_model*, uint8_t*, rjp_cell*, uint8_t*, int32_t*, int32_t,
+int rjp_launch_fill(const rjp_model*, uint8_t*, rjp_cell*, uint8_t*, int32_t*, int32_t*, int32_t,
                     int32_t*, int32_t*, cudaStream_t);
 long long rjp_launch_brick_count(const rjp_model*);
 int rjp_launch_patch(const rjp_model*, const int64_t*, const uint8_t*, int32_t, uint8_t*,
@@ -83,13 +83,14 @@ extern "C" int64_t rjp_brick_count(const rjp_model* m) {
 }
 
 extern "C" int rjp_fill_grid(const rjp_model* m, uint8_t* nverts, rjp_cell* cells,
-                             uint8_t* brick_state, int32_t* ties, int32_t tie_capacity,
-                             int32_t* n_ties, int32_t* extents, void* stream) {
+                             uint8_t* brick_state, int32_t* brick_work, int32_t* ties,
+                             int32_t tie_capacity, int32_t* n_ties, int32_t* extents,
+                             void* stream) {
   if (!model_ok(m) || !nverts || !cells || !n_ties || !extents || tie_capacity < 0 ||
       (tie_capacity > 0 && !ties))
     return RJP_ERR_ARG;
-  return check_launch(rjp_launch_fill(m, nverts, cells, brick_state, ties, tie_capacity, n_ties,
-                                      extents, (cudaStream_t)stream));
+  return check_launch(rjp_launch_fill(m, nverts, cells, brick_state, brick_work, ties,
+                                      tie_capacity, n_ties, extents, (cudaStream_t)stream));
 }
 
 extern "C" int rjp_patch_cells(const rjp_model* m, const int64_t* cell_idx,

@@ -48,6 +48,82 @@ __device__ inline bool brick_outside(const rjp_model& m, int tx0, int ty0, int t
   return rh > 0.0 && (c.w - rb) > m.w0 * pow(rh, m.eps) * (1.0 + 1e-6);
 }
 
+// All-zero brick (outside the jet) into a buffer that holds other data there.
+__device__ __forceinline__ void brick_zero(const rjp_model& m, int tx0, int ty0, int tz0,
+                                           uint8_t* __restrict__ nverts,
+                                           rjp_cell* __restrict__ cells) {
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+  for (int lx = 0; lx < TX; ++lx) {
+    const int ix = tx0 + lx, iy = ty0 + wrp, iz = tz0 + lane;
+    if (ix >= m.x_hi || iy >= m.ny || iz >= m.nz) continue;
+    const size_t idx = ((size_t)(ix - m.x_lo) * m.ny + iy) * m.nz + iz;
+    nverts[idx] = 0;
+    reinterpret_cast<double2*>(cells)[idx] = make_double2(0.0, 0.0);
+  }
+}
+
+// One brick that may intersect the jet: vertex tests into s_in, then the cells.  Called by
+// all FILL_THREADS threads of the CTA; ends with a barrier (s_in can be reused).
+__device__ __forceinline__ void brick_compute(const rjp_model& m, int tx0, int ty0, int tz0,
+                                              uint8_t* s_in, uint8_t* __restrict__ nverts,
+                                              rjp_cell* __restrict__ cells,
+                                              int32_t* __restrict__ ties, int32_t tie_capacity,
+                                              int32_t* __restrict__ n_ties,
+                                              int32_t* __restrict__ extents) {
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  for (int v = threadIdx.x; v < NVERT; v += FILL_THREADS) {
+    const int lz = v % (TZ + 1);
+    const int ly = (v / (TZ + 1)) % (TY + 1);
+    const int lx = v / ((TZ + 1) * (TY + 1));
+    const int I = tx0 + lx, J = ty0 + ly, K = tz0 + lz;
+    int res = 0;
+    if (I <= m.x_hi && J <= m.ny && K <= m.nz) {
+      res = vertex_inside(m, corner(m.cs, I, m.nx), corner(m.cs, J, m.ny),
+                          corner(m.cs, K, m.nz));
+      // report each near-tie once: by the brick that owns the vertex (lower faces),
+      // or by the last brick at the slab / grid upper faces
+      const bool own = (lx < TX || I == m.x_hi) && (ly < TY || J == m.ny) &&
+                       (lz < TZ || K == m.nz);
+      if ((res & 2) && own) {
+        const int slot = atomicAdd(n_ties, 1);
+        if (slot < tie_capacity) {
+          ties[4 * slot + 0] = I;
+          ties[4 * slot + 1] = J;
+          ties[4 * slot + 2] = K;
+          ties[4 * slot + 3] = res & 1;
+        }
+      }
+    }
+    s_in[v] = (uint8_t)(res & 1);
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int lx = 0; lx < TX; ++lx) {
+    const int ix = tx0 + lx, iy = ty0 + wrp, iz = tz0 + lane;  // warp index == local y
+    if (ix >= m.x_hi || iy >= m.ny || iz >= m.nz) continue;
+    int cnt = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int vx = lx + (c & 1), vy = wrp + ((c >> 1) & 1), vz = lane + (c >> 2);
+      cnt += s_in[(vx * (TY + 1) + vy) * (TZ + 1) + vz];
+    }
+    const size_t idx = ((size_t)(ix - m.x_lo) * m.ny + iy) * m.nz + iz;
+    nverts[idx] = (uint8_t)cnt;
+    rjp_cell c = {0.0, 0.0};
+    if (cnt > 0) {
+      c = pack_cell(m, ix, iy, iz, cnt);
+      // y-extent of the ray's in-jet cells, for the ray kernels of the integration pass
+      int32_t* e = extents + 2 * ((size_t)(ix - m.x_lo) * m.nz + iz);
+      atomicMin(e, iy);
+      atomicMax(e + 1, iy + 1);
+    }
+    reinterpret_cast<double2*>(cells)[idx] = make_double2(c.ne0, c.temp);
+  }
+  __syncthreads();   // s_in is reused by the next brick
+}
+
 __global__ void __launch_bounds__(FILL_THREADS)
 fill_grid_kernel(const rjp_model m, uint8_t* __restrict__ nverts,
                  rjp_cell* __restrict__ cells, uint8_t* __restrict__ brick_state,
@@ -64,7 +140,6 @@ fill_grid_kernel(const rjp_model m, uint8_t* __restrict__ nverts,
   const int bz = t % tiles_z; t /= tiles_z;
   const int sy = t % sup_y;
   const int sx = t / sup_y;
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
 
   if (threadIdx.x < SBX * SBY) {
     const int bx = sx * SBX + threadIdx.x / SBY, by = sy * SBY + threadIdx.x % SBY;
@@ -86,68 +161,67 @@ fill_grid_kernel(const rjp_model m, uint8_t* __restrict__ nverts,
     const int tx0 = m.x_lo + (sx * SBX + k / SBY) * TX;
     const int ty0 = (sy * SBY + k % SBY) * TY;
     const int tz0 = bz * TZ;
-    if (todo == 1) {
-#pragma unroll
-      for (int lx = 0; lx < TX; ++lx) {
-        const int ix = tx0 + lx, iy = ty0 + wrp, iz = tz0 + lane;
-        if (ix >= m.x_hi || iy >= m.ny || iz >= m.nz) continue;
-        const size_t idx = ((size_t)(ix - m.x_lo) * m.ny + iy) * m.nz + iz;
-        nverts[idx] = 0;
-        reinterpret_cast<double2*>(cells)[idx] = make_double2(0.0, 0.0);
-      }
-      continue;
-    }
+    if (todo == 1) brick_zero(m, tx0, ty0, tz0, nverts, cells);
+    else brick_compute(m, tx0, ty0, tz0, s_in, nverts, cells, ties, tie_capacity, n_ties, extents);
+  }
+}
 
-    for (int v = threadIdx.x; v < NVERT; v += FILL_THREADS) {
-      const int lz = v % (TZ + 1);
-      const int ly = (v / (TZ + 1)) % (TY + 1);
-      const int lx = v / ((TZ + 1) * (TY + 1));
-      const int I = tx0 + lx, J = ty0 + ly, K = tz0 + lz;
-      int res = 0;
-      if (I <= m.x_hi && J <= m.ny && K <= m.nz) {
-        res = vertex_inside(m, corner(m.cs, I, m.nx), corner(m.cs, J, m.ny),
-                            corner(m.cs, K, m.nz));
-        // report each near-tie once: by the brick that owns the vertex (lower faces),
-        // or by the last brick at the slab / grid upper faces
-        const bool own = (lx < TX || I == m.x_hi) && (ly < TY || J == m.ny) &&
-                         (lz < TZ || K == m.nz);
-        if ((res & 2) && own) {
-          const int slot = atomicAdd(n_ties, 1);
-          if (slot < tie_capacity) {
-            ties[4 * slot + 0] = I;
-            ties[4 * slot + 1] = J;
-            ties[4 * slot + 2] = K;
-            ties[4 * slot + 3] = res & 1;
-          }
-        }
-      }
-      s_in[v] = (uint8_t)(res & 1);
-    }
+// Two-level sparse fill (needs the occupancy map and a work list from the caller): one thread
+// per brick classifies it and appends the bricks that need work to a list; a persistent grid
+// then pulls bricks from the list one at a time, so the ~3 % of bricks around the jet are
+// spread evenly over the SMs (the one-kernel fill above leaves them to ~3 % of its CTAs).
+// work[0] = list length, work[1] = cursor, work[4 + k] = 2 * brick id + (1 if compute).
+__global__ void __launch_bounds__(256)
+fill_classify_kernel(const rjp_model m, uint8_t* __restrict__ brick_state,
+                     int32_t* __restrict__ work, long long nbricks) {
+  const long long bid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int tiles_y = (m.ny + TY - 1) / TY;
+  const int tiles_z = (m.nz + TZ - 1) / TZ;
+  int todo = 0;
+  if (bid < nbricks) {
+    const int bz = (int)(bid % tiles_z);
+    const int by = (int)((bid / tiles_z) % tiles_y);
+    const int bx = (int)(bid / ((long long)tiles_z * tiles_y));
+    const bool out = brick_outside(m, m.x_lo + bx * TX, by * TY, bz * TZ);
+    const bool holds_data = brick_state[bid] != 0;
+    todo = out ? (holds_data ? 1 : 0) : 2;
+    brick_state[bid] = out ? 0 : 1;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, todo != 0);
+  if (bal == 0u) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(work, __popc(bal));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (todo != 0)
+    work[4 + base + __popc(bal & ((1u << lane) - 1u))] = (int32_t)(bid * 2 + (todo == 2 ? 1 : 0));
+}
+
+__global__ void __launch_bounds__(FILL_THREADS)
+fill_bricks_kernel(const rjp_model m, uint8_t* __restrict__ nverts, rjp_cell* __restrict__ cells,
+                   int32_t* __restrict__ ties, int32_t tie_capacity,
+                   int32_t* __restrict__ n_ties, int32_t* __restrict__ extents,
+                   int32_t* __restrict__ work) {
+  __shared__ uint8_t s_in[NVERT];
+  __shared__ int s_next;
+  const int tiles_y = (m.ny + TY - 1) / TY;
+  const int tiles_z = (m.nz + TZ - 1) / TZ;
+  const int n = work[0];
+  for (;;) {
+    if (threadIdx.x == 0) s_next = atomicAdd(work + 1, 1);
     __syncthreads();
-
-#pragma unroll
-    for (int lx = 0; lx < TX; ++lx) {
-      const int ix = tx0 + lx, iy = ty0 + wrp, iz = tz0 + lane;  // warp index == local y
-      if (ix >= m.x_hi || iy >= m.ny || iz >= m.nz) continue;
-      int cnt = 0;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int vx = lx + (c & 1), vy = wrp + ((c >> 1) & 1), vz = lane + (c >> 2);
-        cnt += s_in[(vx * (TY + 1) + vy) * (TZ + 1) + vz];
-      }
-      const size_t idx = ((size_t)(ix - m.x_lo) * m.ny + iy) * m.nz + iz;
-      nverts[idx] = (uint8_t)cnt;
-      rjp_cell c = {0.0, 0.0};
-      if (cnt > 0) {
-        c = pack_cell(m, ix, iy, iz, cnt);
-        // y-extent of the ray's in-jet cells, for the ray kernels of the integration pass
-        int32_t* e = extents + 2 * ((size_t)(ix - m.x_lo) * m.nz + iz);
-        atomicMin(e, iy);
-        atomicMax(e + 1, iy + 1);
-      }
-      reinterpret_cast<double2*>(cells)[idx] = make_double2(c.ne0, c.temp);
-    }
-    __syncthreads();   // s_in is reused by the next brick
+    const int k = s_next;
+    __syncthreads();
+    if (k >= n) break;
+    const int entry = work[4 + k];
+    const long long bid = entry >> 1;
+    const int tz0 = (int)(bid % tiles_z) * TZ;
+    const int ty0 = (int)((bid / tiles_z) % tiles_y) * TY;
+    const int tx0 = m.x_lo + (int)(bid / ((long long)tiles_z * tiles_y)) * TX;
+    if (entry & 1)
+      brick_compute(m, tx0, ty0, tz0, s_in, nverts, cells, ties, tie_capacity, n_ties, extents);
+    else
+      brick_zero(m, tx0, ty0, tz0, nverts, cells);
   }
 }
 
@@ -245,12 +319,24 @@ extern "C" long long rjp_launch_brick_count(const rjp_model* m) {
 }
 
 extern "C" int rjp_launch_fill(const rjp_model* m, uint8_t* nverts, rjp_cell* cells,
-                               uint8_t* brick_state, int32_t* ties, int32_t tie_capacity,
-                               int32_t* n_ties, int32_t* extents, cudaStream_t stream) {
+                               uint8_t* brick_state, int32_t* brick_work, int32_t* ties,
+                               int32_t tie_capacity, int32_t* n_ties, int32_t* extents,
+                               cudaStream_t stream) {
   const int nxs = m->x_hi - m->x_lo;
   const size_t nray = (size_t)nxs * m->nz;
   init_extents_kernel<<<(unsigned)((nray + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<int2*>(extents), nray);
+  if (brick_state != nullptr && brick_work != nullptr) {
+    const long long nb = rjp_launch_brick_count(m);
+    if (nb <= 0 || nb >= (1LL << 30)) return RJP_ERR_ARG;
+    cudaMemsetAsync(brick_work, 0, 4 * sizeof(int32_t), stream);
+    fill_classify_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(*m, brick_state,
+                                                                          brick_work, nb);
+    fill_bricks_kernel<<<148 * 6, FILL_THREADS, 0, stream>>>(*m, nverts, cells, ties,
+                                                             tie_capacity, n_ties, extents,
+                                                             brick_work);
+    return RJP_OK;
+  }
   const int tiles_x = (nxs + TX - 1) / TX, tiles_y = (m->ny + TY - 1) / TY;
   const long long sup = (long long)((tiles_x + SBX - 1) / SBX) * ((tiles_y + SBY - 1) / SBY) *
                         ((m->nz + TZ - 1) / TZ);

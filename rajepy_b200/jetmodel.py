@@ -576,6 +576,7 @@ class JetModel:
             nbricks = int(lib.rjp_brick_count(m))
             nverts, cells, bricks = _take_state(torch, dev, ncell, nbricks)
             ties = torch.empty((_TIE_CAPACITY, 4), dtype=torch.int32, device=dev)
+            work = torch.empty(nbricks + 4, dtype=torch.int32, device=dev)   # fill work list
             counters = torch.zeros(8, dtype=torch.int32, device=dev)  # [0] n_ties
             nray = (self._x_hi - self._x_lo) * self._nz
             extents = torch.empty((nray, 2), dtype=torch.int32, device=dev)
@@ -583,10 +584,11 @@ class JetModel:
             for attempt in range(3):
                 counters.zero_()
                 st = lib.rjp_fill_grid(m, nverts.data_ptr(), cells.data_ptr(),
-                                       bricks.data_ptr(), ties.data_ptr(), tie_cap,
+                                       bricks.data_ptr(), work.data_ptr(), ties.data_ptr(),
+                                       tie_cap,
                                        counters.data_ptr(), extents.data_ptr(), self._stream())
                 _cabi.check(st, "rjp_fill_grid")
-                _launched(2)   # init_extents_kernel + fill_grid_kernel
+                _launched(3)   # init_extents, fill_classify, fill_bricks kernels
                 c = counters.cpu().numpy()
                 if c[0] <= tie_cap:
                     break

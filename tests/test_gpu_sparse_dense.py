@@ -76,7 +76,7 @@ def test_recycled_state_equals_dense_fill():
     ext = torch.empty_like(d["extents"])
     ties = torch.empty((1 << 16, 4), dtype=torch.int32, device="cuda")
     cnt = torch.zeros(8, dtype=torch.int32, device="cuda")
-    st = lib.rjp_fill_grid(d["model"], nv.data_ptr(), cl.data_ptr(), None, ties.data_ptr(),
+    st = lib.rjp_fill_grid(d["model"], nv.data_ptr(), cl.data_ptr(), None, None, ties.data_ptr(),
                            1 << 16, cnt.data_ptr(), ext.data_ptr(), second._stream())
     _cabi.check(st, "rjp_fill_grid(dense)")
     torch.cuda.synchronize()

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
             "rjp_continuum_images", "rjp_strerror"} <= declared
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in the header but not exported"
-    assert lib.rjp_abi_version() == 3
+    assert lib.rjp_abi_version() == 4
     assert lib.rjp_strerror(0) == b"ok"
     assert lib.rjp_strerror(-1) == b"invalid argument"
 
@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_rejects_bad_arguments_without_gpu():
     lib = _cabi.load()
     m = _cabi.Model()  # all zero: invalid dims
-    assert lib.rjp_fill_grid(m, None, None, None, None, 0, None, None, None) == _cabi.ERR_ARG
+    assert lib.rjp_fill_grid(m, None, None, None, None, None, 0, None, None, None) == _cabi.ERR_ARG
     assert lib.rjp_brick_count(m) < 0
     assert lib.rjp_voigt_profile(None, None, 5, None, None) == _cabi.ERR_ARG
     assert lib.rjp_continuum_images(None, None, None, 0, None, None, 1.0, 0, None, None,

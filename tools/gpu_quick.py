@@ -28,6 +28,7 @@ def timed(fn, n=3):
 
 
 SPARSE = "--dense-fill" not in sys.argv
+TWO_LEVEL = "--one-level-fill" not in sys.argv
 
 
 def main():
@@ -51,11 +52,14 @@ def main():
         injet = int((d["nverts"] > 0).sum())
         lib = rb._cabi.load()
 
+        work = torch.empty(d["bricks"].numel() + 4, dtype=torch.int32, device="cuda")
+
         def refill():
             cnt = torch.zeros(8, dtype=torch.int32, device="cuda")
             ties = torch.empty((1 << 16, 4), dtype=torch.int32, device="cuda")
             lib.rjp_fill_grid(d["model"], d["nverts"].data_ptr(), d["cells"].data_ptr(),
                               d["bricks"].data_ptr() if SPARSE else None,
+                              work.data_ptr() if (SPARSE and TWO_LEVEL) else None,
                               ties.data_ptr(), 1 << 16, cnt.data_ptr(),
                               d["extents"].data_ptr(), jm._stream())
         t_fill = timed(refill)
