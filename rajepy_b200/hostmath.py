@@ -278,3 +278,57 @@ def chan_freqs(freq, bandwidth, chanwidth):
     nchan = int(bandwidth / chanwidth)
     chan1 = freq - bandwidth / 2. + chanwidth / 2.
     return chan1 + np.arange(nchan) * chanwidth
+
+
+# ----------------------------------------------------------------- Reynolds (1986) cross-check
+A_K = 0.212      # _constants.py:13
+A_J = 6.5e-38    # _constants.py:14
+
+
+def flux_expected_r86(jm, freq, which, y_max, y_min=None):
+    """Exact flux [Jy] of one lobe of the jet from equation 8 of Reynolds (1986), between the
+    angular distances y_min and y_max [arcsec] from the jet base (maths/physics.py:297-374).
+    `jm` is a JetModel (only its parameters and steady-state mass-loss rates are read): the
+    analytic sanity check the reference overlays on its SED plots
+    (plotting/functions.py:1198-1199)."""
+    from mpmath import gammainc
+    p = jm.params
+    inc = p['geometry']['inc']
+    w_0 = p['geometry']['w_0'] * con.au * 1e2
+    t_0 = p['properties']['T_0']
+    n_0 = p['properties']['n_0']
+    if which == 'R':
+        n_0 *= jm.ss_jml('R') / jm.ss_jml('B')
+    x_0 = p['properties']['x_0']
+    q_tau_ = p["power_laws"]["q_tau"]
+    q_t = p["power_laws"]["q_T"]
+    eps = p["geometry"]["epsilon"]
+    mod_r_0 = p['geometry']['mod_r_0'] * con.au * 1e2
+    mod_y_0 = mod_r_0 * np.sin(np.radians(inc))
+    r_0 = p['geometry']['r_0'] * con.au * 1e2
+    y_0 = r_0 * np.sin(np.radians(inc))
+    d = p['target']['dist'] * con.parsec * 1e2
+    if p["power_laws"]["q^d_n"] != 0.:
+        mlr = p["properties"]["mlr"] * 1.989e30 / con.year
+        n_0 = mlr / (np.pi * p['properties']['mu'] * atomic_mass("H") * w_0 ** 2. *
+                     p['properties']["v_0"] * 1e5)
+    y_max = np.tan(y_max * con.arcsec) * d + mod_y_0 - y_0
+    if y_min is not None:
+        y_min = np.tan(y_min * con.arcsec) * d + mod_y_0 - y_0
+    else:
+        y_min = mod_y_0
+    tau_0 = 2. * A_K * w_0 * (n_0 * x_0) ** 2. * t_0 ** -1.35 * freq ** -2.1 * \
+        np.sin(np.radians(inc)) ** -1.
+    c = 1. + eps + q_t
+
+    def indef_integral(yval):
+        const = 2. * w_0 * d ** -2. * A_J * A_K ** -1. * t_0 * freq ** 2.
+        rho_ = yval / mod_y_0
+        tau = tau_0 * rho_ ** q_tau_
+        p1 = yval / (q_tau_ * c) * rho_ ** (c - 1.) * tau ** (-c / q_tau_)
+        p2 = q_tau_ * tau ** (c / q_tau_) + c * gammainc(c / q_tau_, tau)
+        return const * (float(p1) * float(p2))
+
+    flux = indef_integral(y_max) - indef_integral(y_min)
+    flux *= 1e-7 * 1e2 ** 2.
+    return flux / 1e-26

@@ -218,3 +218,18 @@ def test_sharded_models_agree_on_work_balanced_slabs():
     assert min(widths[1:3]) < min(widths[0], widths[3])      # the jet sits in the middle planes
     even = [_model(p, shard=(r, 4), balance=False).slab for r in range(4)]
     assert even == [(0, 16), (16, 32), (32, 48), (48, 64)]
+
+
+def test_reynolds_1986_analytic_flux_matches_reference():
+    """maths/physics.py:297-374 restated in hostmath against values computed by the unmodified
+    reference (tests/golden/r86.npz, tools/make_golden_r86.py)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "r86.npz"))
+    for name in ("small", "inclined", "nobursts", "tgrad"):
+        jm = _model(cases.CASES[name][0]())
+        for i, f in enumerate(g["freqs"]):
+            for j, which in enumerate("RB"):
+                for k, ymax in enumerate(g["ymax"]):
+                    for m, ymin in enumerate((None, 0.05)):
+                        got = hm.flux_expected_r86(jm, float(f), which, float(ymax), ymin)
+                        assert got == pytest.approx(g[name][i, j, k, m], rel=1e-12), \
+                            (name, f, which, ymax, ymin)
