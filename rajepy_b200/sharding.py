@@ -61,7 +61,7 @@ def gather_x(tile, nx, rank, world, dim=0, group=None, bounds=None):
     """All-gather x-slab tiles along dimension `dim` into the full array (every rank gets
     the full result).  `tile` is a torch tensor on the device NCCL/gloo is bound to.
 
-    Equal slabs (the normal case) need no staging copy at all: the tiles are gathered
+    Equal slabs need no staging copy at all: the tiles are gathered
     as they are into a (world, ...) buffer and the result is returned as a VIEW of it with
     the rank axis folded into x (for dim > 0 the view is non-contiguous; consumers that
     need contiguity copy once, e.g. straight into pinned host memory)."""
@@ -83,19 +83,18 @@ def gather_x(tile, nx, rank, world, dim=0, group=None, bounds=None):
         shape = list(tile.shape)
         shape[dim] = world * big
         return out.reshape(shape) if dim == 0 else _fold(out, dim)
-    # uneven split: pad to the largest slab (collectives need equal sizes)
-    if dim != 0:
-        tile = tile.movedim(dim, 0).contiguous()
-    if tile.shape[0] < big:
-        pad = torch.zeros([big - tile.shape[0]] + list(tile.shape[1:]), dtype=tile.dtype,
-                          device=tile.device)
-        tile = torch.cat([tile, pad], dim=0)
-    out = torch.empty([world * big] + list(tile.shape[1:]), dtype=tile.dtype,
-                      device=tile.device)
-    dist.all_gather_into_tensor(out, tile, group=group)
-    out = torch.cat([out[r * big: r * big + sizes[r]] for r in range(world)], dim=0)
-    if dim != 0:
-        out = out.movedim(0, dim).contiguous()
+    # uneven split (work-balanced slabs differ by up to two orders of magnitude in width, so
+    # padding every tile to the widest slab would move mostly padding): every rank drops its
+    # tile into a zero-filled full-size array and the arrays are summed.  x + 0 is exact (and
+    # NaN + 0 stays NaN), so the result is bit-identical to a gather, up to the sign of zero.
+    los = [0]
+    for sz in sizes:
+        los.append(los[-1] + sz)
+    shape = list(tile.shape)
+    shape[dim] = los[-1]
+    out = torch.zeros(shape, dtype=tile.dtype, device=tile.device)
+    out.narrow(dim, los[rank], sizes[rank]).copy_(tile)
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
     return out
 
 
