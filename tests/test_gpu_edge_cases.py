@@ -1,0 +1,89 @@
+"""Edge cases of the line-of-sight pass against the numpy oracle: channel lists that are not
+equally spaced (the kernels then read the offsets instead of forming them), more channels
+than one launch holds (channel blocks), channel counts that do not fill the last group,
+a single channel, and a grid that no ray of which crosses the jet."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import scipy.constants as con
+
+from tests import cases
+from tests.parity import assert_parity, cancellation_floor_ff, cancellation_floor_line
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(params):
+    import rajepy_b200 as rb
+    from oracle import rajepy_oracle as orc
+    log = rb.logger.Log(os.path.join(tempfile.mkdtemp(), "m.log"), verbose=False)
+    return rb.JetModel(params, log=log), orc.OracleJet(params)
+
+
+def _check_cubes(jm, oj, chans):
+    tau = assert_parity(jm.optical_depth_rrl('H58a', chans), oj.optical_depth_rrl('H58a', chans),
+                        "tau_rrl", floor=1e-290)
+    fl = np.nan_to_num(cancellation_floor_line(oj, chans) + cancellation_floor_ff(oj, chans),
+                       nan=0.0, posinf=0.0)
+    assert_parity(jm.flux_rrl('H58a', chans, contsub=False),
+                  oj.flux_rrl('H58a', chans, contsub=False), "S_rrl", floor=fl)
+    return tau
+
+
+def test_unequally_spaced_channels():
+    from oracle import rajepy_oracle as orc
+    jm, oj = _pair(cases.case_small())
+    jm.time = oj.time = 1.0 * con.year
+    nu0 = orc.rrl_nu_0('H', 58, 1)
+    rng = np.random.default_rng(11)
+    chans = np.sort(nu0 + rng.uniform(-1.2e7, 1.2e7, 45))
+    ln = jm._line_structs('H58a', chans, jm._device())[0]
+    assert ln.chan_step == 0.0                       # takes the table-reading instantiation
+    assert _check_cubes(jm, oj, chans) < 2e-7
+    even = cases.line_channels(nu0, 45, 3e5)
+    assert jm._line_structs('H58a', even, jm._device())[0].chan_step == pytest.approx(3e5)
+
+
+@pytest.mark.parametrize("nchan", [1, 7, 37, 130])
+def test_partial_channel_groups(nchan):
+    from oracle import rajepy_oracle as orc
+    jm, oj = _pair(cases.case_small())
+    jm.time = oj.time = 0.7 * con.year
+    chans = cases.line_channels(orc.rrl_nu_0('H', 58, 1), nchan, 4e5)
+    _check_cubes(jm, oj, chans)
+
+
+def test_more_channels_than_one_launch():
+    """2100 channels: two channel blocks (8 channels x 256 threads per launch)."""
+    from oracle import rajepy_oracle as orc
+    p = cases.with_grid(cases.base_params(), 12, 28, 36)
+    jm, oj = _pair(p)
+    jm.time = oj.time = 0.4 * con.year
+    chans = cases.line_channels(orc.rrl_nu_0('H', 58, 1), 2100, 2e4)
+    got = jm.optical_depth_rrl('H58a', chans)
+    ref = oj.optical_depth_rrl('H58a', chans)
+    assert_parity(got, ref, "tau_rrl 2100 channels", floor=1e-290)
+    assert_parity(jm.flux_rrl('H58a', chans, contsub=False),
+                  oj.flux_rrl('H58a', chans, contsub=False), "S_rrl 2100 channels",
+                  floor=np.nan_to_num(cancellation_floor_line(oj, chans) +
+                                      cancellation_floor_ff(oj, chans), nan=0.0, posinf=0.0))
+
+
+def test_grid_that_misses_the_jet():
+    """Launch radius beyond the grid: no cell is inside the jet, every product is the
+    reference's constant (EM = tau = 0, intensity / flux NaN)."""
+    p = cases.with_grid(cases.base_params(), 16, 20, 24)
+    p["geometry"]["r_0"] = 500.
+    jm, oj = _pair(p)
+    assert int(jm.n_verts_inside().sum()) == 0 == int(oj.n_verts_inside().sum())
+    assert jm._ensure_filled()["n_active"] == 0
+    chans = cases.line_channels(3.285e10, 9, 1e6)
+    assert np.array_equal(jm.emission_measure(), np.zeros((16, 24)))
+    assert np.array_equal(jm.optical_depth_ff(np.array([5e9, 1e10])), np.zeros((2, 16, 24)))
+    assert np.isnan(jm.flux_ff(5e9)).all()
+    assert np.array_equal(jm.optical_depth_rrl('H58a', chans), np.zeros((9, 16, 24)))
+    assert np.isnan(jm.flux_rrl('H58a', chans, contsub=False)).all()
+    lm = jm.los_means()
+    assert np.isnan(lm["number_density"]).all() and np.isnan(lm["n_max"])
