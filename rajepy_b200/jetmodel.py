@@ -1252,8 +1252,8 @@ class JetModel:
         scalar = np.isscalar(freq)
         freqs = np.atleast_1d(np.asarray(freq, dtype=np.float64))
         if not collapse:
-            raise NotImplementedError("collapse=False (per-cell RRL optical depths) is not "
-                                      "provided by the CUDA path")
+            tau = self._cellwise_tau_rrl(rrl, freqs)
+            return tau[0] if scalar else tau
         res = self._pass(rrl, freqs, contsub=self._line_contsub_hint(), want_tau=True,
                          want_flux=True)
         tau = self._host_image(res["tau"], lead=freqs.size)
@@ -1302,6 +1302,31 @@ class JetModel:
         if savefits:
             self._save_image(fluxes, savefits, 'flux', freq, scalar)
         return fluxes
+
+    def _cellwise_tau_rrl(self, rrl, freqs):
+        """`optical_depth_rrl(..., collapse=False)` (classes.py:1159-1189, rrls.py:329-389):
+        un-summed (nfreq, nx, ny, nz) line optical depths, composed on the host from the fp64
+        field planes with scipy's wofz (never used by Pipeline; not a hot path)."""
+        from scipy.special import wofz
+        element, n, dn = hm.rrl_parser(rrl)
+        with np.errstate(all='ignore'):
+            rest = hm.rrl_nu_0(element, n, dn) * (1. - self.vel[1] * 1000. / con.c)
+            n_es = self.number_density * self.ion_fraction
+            t = self.temperature
+            fwhm_g = hm.deltanu_g(rest, t, element)
+            fwhm_l = hm.deltanu_l(n_es, n, dn)
+            sigma = fwhm_g / 2. / np.sqrt(2. * np.log(2))
+            n_i = hm.ni_from_ne(n_es, element)
+            path = self._csize * con.au * 1e2 * (self.fill_factor / self.areas)
+            fn, en, z = hm.f_n1n2(n, dn), hm.energy_n(n, element), hm.z_number(element)
+            out = np.empty((len(freqs),) + n_es.shape)
+            for i, f in enumerate(freqs):
+                phi = np.real(wofz(((f - rest) + 1j * fwhm_l / 2.) / sigma / np.sqrt(2.))) / \
+                    sigma / np.sqrt(2. * np.pi)
+                out[i] = 1.0991132675738456e-17 * (n ** 2. * fn * phi) * \
+                    (n_es * n_i / t ** 1.5) * np.exp((z ** 2. * en) / (hm.k_cgs * t)) * \
+                    (1. - np.exp(-hm.h_cgs * f / (hm.k_cgs * t))) * path
+        return out
 
     def _cellwise_tau_ff(self, freqs):
         """collapse=False branch of optical_depth_ff (classes.py:1383, :1395-1397): the

@@ -87,3 +87,21 @@ def test_grid_that_misses_the_jet():
     assert np.isnan(jm.flux_rrl('H58a', chans, contsub=False)).all()
     lm = jm.los_means()
     assert np.isnan(lm["number_density"]).all() and np.isnan(lm["n_max"])
+
+
+def test_uncollapsed_optical_depths():
+    """collapse=False (classes.py:1173-1177, :1379-1383): per-cell optical depths."""
+    from oracle import rajepy_oracle as orc
+    jm, oj = _pair(cases.case_small())
+    jm.time = oj.time = 1.0 * con.year
+    chans = cases.line_channels(orc.rrl_nu_0('H', 58, 1), 3, 2e6)
+    got = jm.optical_depth_rrl('H58a', chans, collapse=False)
+    ref = oj.optical_depth_rrl('H58a', chans, collapse=False)
+    assert got.shape == ref.shape == (3, jm.nx, jm.ny, jm.nz)
+    assert_parity(got, ref, "tau_rrl cells", rtol=1e-9)
+    assert_parity(jm.optical_depth_rrl('H58a', float(chans[1]), collapse=False), ref[1],
+                  "tau_rrl cells scalar", rtol=1e-9)
+    assert_parity(np.nansum(got, axis=2), jm.optical_depth_rrl('H58a', chans), "sum == collapsed")
+    f = np.array([5e9, 4.3e10])
+    assert_parity(jm.optical_depth_ff(f, collapse=False), oj.optical_depth_ff(f, collapse=False),
+                  "tau_ff cells", rtol=1e-9)
