@@ -809,7 +809,10 @@ extern "C" int rjp_launch_ray_list(const int32_t* extents, int nray, int32_t* li
 // waits until the other one has drained (measured: the channel loop started 0.9 ms late
 // behind the constant writer, which uses no shared memory).
 static void set_carveouts() {
-  static bool done = false;
+  static bool done_on[64] = {};   // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& done = done_on[dev & 63];
   if (done) return;
   const int pct = 75;
   cudaFuncSetAttribute(missed_rays_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
