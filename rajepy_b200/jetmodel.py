@@ -1376,6 +1376,31 @@ class JetModel:
         return None
 
 
+def flux_ff_time_series(params, epochs_s, freq, rank=0, world=1, device=None, log=None,
+                        host=True):
+    """Continuum flux images of a variable-ejection time series (BASELINE config 4; what
+    Pipeline does per run year, classes.py:2347-2453): (n_epochs, nx, nz) at frequency `freq`
+    for the model times `epochs_s` [s].  Sharded by EPOCH: every rank holds the whole grid
+    (epochs only change the burst factor chi(t), the filled state is reused), integrates the
+    epochs `sharding.epoch_shares` deals to it and the images are all-gathered."""
+    from .sharding import epoch_shares, gather_epochs
+    torch = _torch()
+    epochs_s = np.asarray(epochs_s, dtype=np.float64)
+    jm = JetModel(params, log=log, device=device)
+    mine = epoch_shares(len(epochs_s), rank, world)
+    imgs = []
+    for e in mine:
+        jm.time = float(epochs_s[e])
+        imgs.append(jm._continuum_images_device(float(freq), 'flux')[0])
+    dev = jm._device()
+    npix = jm.nx * jm.nz
+    local = torch.stack(imgs) if imgs else torch.empty((0, npix), dtype=torch.float64,
+                                                       device=dev)
+    full = gather_epochs(local, len(epochs_s), rank, world).view(len(epochs_s), jm.nx, jm.nz)
+    jm.release()
+    return _to_host(full) if host else full
+
+
 def _to_host(t):
     """Device tensor -> numpy through a pinned staging buffer."""
     torch = _torch()

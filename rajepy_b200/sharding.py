@@ -57,6 +57,24 @@ def epoch_shares(n_epochs, rank, world):
     return list(range(rank, n_epochs, world))
 
 
+def gather_epochs(local, n_epochs, rank, world, group=None):
+    """All-gather per-epoch results of a time series whose epochs were dealt round-robin
+    (`epoch_shares`): `local` is (len(epoch_shares(n_epochs, rank, world)), ...) in the order of
+    the rank's own epochs; returns (n_epochs, ...) in epoch order on every rank."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return local
+    nmax = (n_epochs + world - 1) // world
+    pad = torch.zeros((nmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    buf = torch.empty((world,) + tuple(pad.shape), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf.view(-1), pad.view(-1), group=group)
+    # epoch e sits at buf[e % world, e // world]
+    out = buf.transpose(0, 1).reshape((nmax * world,) + tuple(local.shape[1:]))
+    return out[:n_epochs].contiguous()
+
+
 def gather_x(tile, nx, rank, world, dim=0, group=None, bounds=None):
     """All-gather x-slab tiles along dimension `dim` into the full array (every rank gets
     the full result).  `tile` is a torch tensor on the device NCCL/gloo is bound to.

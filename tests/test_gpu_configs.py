@@ -59,6 +59,21 @@ def test_config4_burst_time_series():
     assert max(totals) > 1.05 * totals[0]      # the bursts do brighten the jet
 
 
+def test_config4_time_series_driver():
+    """rajepy_b200.flux_ff_time_series (one fill, one pass per epoch) == per-epoch flux_ff."""
+    import rajepy_b200 as rb
+    p = cases.with_grid(cases.base_params(), 64, 64, 96)
+    epochs = np.linspace(0., 5., 16) * con.year
+    series = rb.flux_ff_time_series(p, epochs, 5e9)
+    assert series.shape == (16, 64, 96)
+    jm = _model(cases.with_grid(cases.base_params(), 64, 64, 96))
+    for e in (0, 5, 15):
+        jm.time = float(epochs[e])
+        ref = jm.flux_ff(5e9)
+        assert np.array_equal(np.isnan(series[e]), np.isnan(ref))
+        assert np.array_equal(np.nan_to_num(series[e]), np.nan_to_num(ref))
+
+
 @pytest.mark.parametrize("n,nch", [(512, 256), (1024, 512)])
 def test_large_grid_properties(n, nch):
     """configs[2] (512^3, 256 channels) and configs[4] (1024^3, 512 channels)."""

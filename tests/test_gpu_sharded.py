@@ -64,6 +64,15 @@ def _worker(rank, world, port, out_dir):
                      device=f"cuda:{rank}", shard=(rank, world), balance=False)
     jm.time = 0.9 * con.year
     ok = ok and np.array_equal(jm.optical_depth_rrl('H58a', chans), res["one"][3])
+    # epoch-sharded time series (BASELINE config 4): every rank gets the whole series
+    epochs = np.linspace(0., 5., 7) * con.year
+    series = rb.flux_ff_time_series(cases.with_grid(cases.base_params(), 64, 96, 128), epochs,
+                                    5e9, rank=rank, world=world, device=f"cuda:{rank}", log=log)
+    one = rb.JetModel(cases.with_grid(cases.base_params(), 64, 96, 128), log=log,
+                      device=f"cuda:{rank}")
+    for e in range(len(epochs)):
+        one.time = float(epochs[e])
+        ok = ok and np.array_equal(np.nan_to_num(series[e]), np.nan_to_num(one.flux_ff(5e9)))
     open(os.path.join(out_dir, f"r{rank}.txt"), "w").write("ok" if ok else "MISMATCH")
     dist.barrier()
     dist.destroy_process_group()

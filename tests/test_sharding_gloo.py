@@ -148,3 +148,31 @@ def test_sparse_cube_exchange(world, bounds):
         assert np.array_equal(np.isnan(out["flux"]), np.isnan(flux))
         assert np.array_equal(np.nan_to_num(out["flux"]), np.nan_to_num(flux))
         assert np.array_equal(out["only"], tau)
+
+
+# ------------------------------------------------------------------ epoch sharding
+def _epoch_worker(rank, world, port, n_epochs, out_dir):
+    import torch
+    import torch.distributed as dist
+    from rajepy_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = sharding.epoch_shares(n_epochs, rank, world)
+    # "image" of epoch e: constant e + pixel ramp
+    local = torch.stack([torch.arange(6, dtype=torch.float64) + 100.0 * e for e in mine]) \
+        if mine else torch.empty((0, 6), dtype=torch.float64)
+    full = sharding.gather_epochs(local, n_epochs, rank, world)
+    np.save(os.path.join(out_dir, f"e{rank}.npy"), full.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_epochs", [(2, 7), (4, 64), (4, 3)])
+def test_epoch_sharded_series_is_reassembled_in_order(world, n_epochs):
+    import torch.multiprocessing as mp
+    tmp = tempfile.mkdtemp()
+    mp.spawn(_epoch_worker, args=(world, _free_port(), n_epochs, tmp), nprocs=world, join=True)
+    want = np.arange(6)[None, :] + 100.0 * np.arange(n_epochs)[:, None]
+    for r in range(world):
+        assert np.array_equal(np.load(os.path.join(tmp, f"e{r}.npy")), want)
