@@ -189,6 +189,12 @@ enum {
 int rjp_cell_field(const rjp_model* m_host, const rjp_epoch* ep_host,
                    const uint8_t* nverts, int32_t field, double* out, void* stream);
 
+/* User-assigned grids (the `temperature` / `ion_fraction` setters, classes.py:936-940,
+ * :994-1000): replace T (field = RJP_FIELD_TEMP) or the ionisation fraction (RJP_FIELD_XI) of
+ * every in-jet cell of the packed state by values[slab cell] (NaN / non-positive = invalid). */
+int rjp_override_cells(const rjp_model* m_host, const uint8_t* nverts, int32_t field,
+                       const double* values, rjp_cell* cells, void* stream);
+
 /* List of the rays whose extent is non-empty (slab-local ray index x_local * nz + z), in
  * arbitrary order: the channel loop launches one CTA per listed ray.  `list` holds up to
  * nray entries, *n_active (device) receives the count.  Call after rjp_fill_grid /

@@ -64,7 +64,7 @@ _lib = None
 EXPORTS = ("rjp_strerror", "rjp_last_cuda_error", "rjp_abi_version", "rjp_struct_sizes",
            "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field", "rjp_ray_list", "rjp_integrate",
            "rjp_continuum_images", "rjp_voigt_profile", "rjp_brick_count", "rjp_pack_rays",
-           "rjp_scatter_rays", "rjp_fill_missed", "rjp_los_means")
+           "rjp_scatter_rays", "rjp_fill_missed", "rjp_los_means", "rjp_override_cells")
 
 
 def library_path():
@@ -101,6 +101,8 @@ def load():
     lib.rjp_patch_cells.argtypes = [C.POINTER(Model), vp, vp, i32, vp, vp, vp, vp, vp]
     lib.rjp_los_means.argtypes = [C.POINTER(Model), C.POINTER(Epoch), vp, vp, vp, i32, vp, vp]
     lib.rjp_los_means.restype = C.c_int
+    lib.rjp_override_cells.argtypes = [C.POINTER(Model), vp, i32, vp, vp, vp]
+    lib.rjp_override_cells.restype = C.c_int
     lib.rjp_brick_count.argtypes = [C.POINTER(Model)]
     lib.rjp_brick_count.restype = i64
     lib.rjp_cell_field.argtypes = [C.POINTER(Model), C.POINTER(Epoch), vp, i32, vp, vp]
@@ -115,7 +117,7 @@ def load():
     lib.rjp_voigt_profile.argtypes = [vp, vp, i64, vp, vp]
     for f in ("rjp_struct_sizes", "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field",
               "rjp_ray_list", "rjp_integrate", "rjp_continuum_images", "rjp_voigt_profile",
-              "rjp_pack_rays", "rjp_scatter_rays", "rjp_fill_missed", "rjp_los_means"):
+              "rjp_pack_rays", "rjp_scatter_rays", "rjp_fill_missed", "rjp_los_means", "rjp_override_cells"):
         getattr(lib, f).restype = C.c_int
     sizes = [i32() for _ in range(6)]
     lib.rjp_struct_sizes(*[C.byref(s) for s in sizes])

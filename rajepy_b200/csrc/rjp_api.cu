@@ -29,6 +29,8 @@ int rjp_launch_continuum_images(const double*, const double*, const int32_t*, in
                                 const double*, const double*, double, int, double*, double*,
                                 double*, cudaStream_t);
 int rjp_launch_voigt_profile(const double*, const double*, int64_t, double*, cudaStream_t);
+int rjp_launch_override(const rjp_model*, const uint8_t*, int32_t, const double*, rjp_cell*,
+                        cudaStream_t);
 int rjp_launch_los_means(const rjp_model*, const rjp_epoch*, const uint8_t*, const int32_t*,
                          const int32_t*, int, double*, cudaStream_t);
 }
@@ -206,4 +208,13 @@ extern "C" int rjp_los_means(const rjp_model* m, const rjp_epoch* ep, const uint
     return RJP_ERR_ARG;
   return check_launch(rjp_launch_los_means(m, ep, nverts, extents, ray_list, n_active, out,
                                            (cudaStream_t)stream));
+}
+
+extern "C" int rjp_override_cells(const rjp_model* m, const uint8_t* nverts, int32_t field,
+                                  const double* values, rjp_cell* cells, void* stream) {
+  if (!model_ok(m) || !nverts || !values || !cells ||
+      (field != RJP_FIELD_TEMP && field != RJP_FIELD_XI))
+    return RJP_ERR_ARG;
+  return check_launch(rjp_launch_override(m, nverts, field, values, cells,
+                                          (cudaStream_t)stream));
 }

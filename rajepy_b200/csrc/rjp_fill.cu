@@ -258,6 +258,32 @@ __global__ void patch_cells_kernel(const rjp_model m, const int64_t* __restrict_
   cells[idx] = c;
 }
 
+// User-assigned temperature / ionisation-fraction grids (the setters of classes.py:936-940,
+// :994-1000): re-pack the state of the in-jet cells from the caller's 3-D array.
+__global__ void __launch_bounds__(256)
+override_cells_kernel(const rjp_model m, const uint8_t* __restrict__ nverts, int field,
+                      const double* __restrict__ values, rjp_cell* __restrict__ cells) {
+  const size_t ncell = (size_t)(m.x_hi - m.x_lo) * m.ny * m.nz;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < ncell;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int cnt = nverts[idx];
+    if (cnt == 0) continue;
+    const double v = values[idx];
+    rjp_cell c = cells[idx];
+    if (field == RJP_FIELD_TEMP) {
+      const double t = (v == v && v > 0.0 && !isinf(v)) ? v : 0.0;
+      c.temp = (cnt < 8) ? -t : t;
+    } else {
+      const int iz = (int)(idx % m.nz);
+      const int iy = (int)((idx / m.nz) % m.ny);
+      const int ix = m.x_lo + (int)(idx / ((size_t)m.nz * m.ny));
+      const double ne0 = laws_of(m, centroid_rw(m, ix, iy, iz), false).nd * v;
+      c.ne0 = (ne0 == ne0 && !isinf(ne0) && ne0 > 0.0) ? ne0 : 0.0;
+    }
+    cells[idx] = c;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 cell_field_kernel(const rjp_model m, const rjp_epoch ep, const uint8_t* __restrict__ nverts,
                   int field, double* __restrict__ out) {
@@ -353,6 +379,16 @@ extern "C" int rjp_launch_patch(const rjp_model* m, const int64_t* cell_idx,
   if (n <= 0) return RJP_OK;
   patch_cells_kernel<<<(n + 127) / 128, 128, 0, stream>>>(*m, cell_idx, new_count, n, nverts,
                                                          cells, brick_state, extents);
+  return RJP_OK;
+}
+
+extern "C" int rjp_launch_override(const rjp_model* m, const uint8_t* nverts, int32_t field,
+                                   const double* values, rjp_cell* cells, cudaStream_t stream) {
+  const size_t ncell = (size_t)(m->x_hi - m->x_lo) * m->ny * m->nz;
+  size_t blocks = (ncell + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  if (blocks == 0) return RJP_OK;
+  override_cells_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*m, nverts, field, values, cells);
   return RJP_OK;
 }
 

@@ -560,9 +560,9 @@ class JetModel:
         the reference's own numpy expression so that the counts are bit-exact."""
         if self._dev is not None:
             return self._dev
-        if self._overrides:
-            raise NotImplementedError("user-assigned grids (ts/ion_fraction/temperature/"
-                                      "vel setters) are not supported by the CUDA path")
+        if 'travel' in self._overrides or 'vel' in self._overrides:
+            raise NotImplementedError("user-assigned `ts` / `vel` grids are not supported by the "
+                                      "CUDA path (`ion_fraction` and `temperature` are)")
         torch = _torch()
         lib = _cabi.load()
         dev = self._device()
@@ -603,6 +603,18 @@ class JetModel:
                          "n_ties": n_ties, "n_patched": 0}
             if n_ties > 0:
                 self._resolve_ties(ties[:n_ties].cpu().numpy().astype(np.int64))
+            for name, field in (('xi', 8), ('temp', 9)):     # RJP_FIELD_XI, RJP_FIELD_TEMP
+                if name in self._overrides:
+                    arr = np.ascontiguousarray(
+                        np.asarray(self._overrides[name], dtype=np.float64)
+                        [self._x_lo:self._x_hi])
+                    if arr.shape != (self._x_hi - self._x_lo, self._ny, self._nz):
+                        raise ValueError(f"assigned grid has shape {arr.shape}")
+                    vals = torch.from_numpy(arr).to(dev)
+                    st = lib.rjp_override_cells(m, nverts.data_ptr(), field, vals.data_ptr(),
+                                                cells.data_ptr(), self._stream())
+                    _cabi.check(st, "rjp_override_cells")
+                    _launched()
             self._build_ray_list()
         if self.log:
             self.log.add_entry(mtype="INFO",
@@ -1065,6 +1077,9 @@ class JetModel:
         'n_min', 'n_max', 't_max' = nanmin / nanmax over the whole grid."""
         torch = _torch()
         lib = _cabi.load()
+        if self._overrides:
+            raise NotImplementedError("los_means() evaluates the model's own power laws; it does "
+                                      "not see user-assigned grids")
         d = self._ensure_filled()
         dev = d["device"]
         npix = (self._x_hi - self._x_lo) * self._nz

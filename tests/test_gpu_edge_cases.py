@@ -105,3 +105,35 @@ def test_uncollapsed_optical_depths():
     f = np.array([5e9, 4.3e10])
     assert_parity(jm.optical_depth_ff(f, collapse=False), oj.optical_depth_ff(f, collapse=False),
                   "tau_ff cells", rtol=1e-9)
+
+
+def test_user_assigned_temperature_and_ion_fraction():
+    """The `temperature` / `ion_fraction` setters (classes.py:936-940, :994-1000): assigning
+    0.5 T and 2 x everywhere must give the products of a jet with T_0 / 2 and 2 x_0."""
+    import copy
+    import rajepy_b200 as rb
+    from oracle import rajepy_oracle as orc
+    log = rb.logger.Log(os.path.join(tempfile.mkdtemp(), "m.log"), verbose=False)
+    p = cases.case_small()
+    jm = rb.JetModel(copy.deepcopy(p), log=log)
+    t3d, x3d = jm.temperature, jm.ion_fraction
+    jm.temperature = 0.5 * t3d
+    jm.ion_fraction = 2.0 * x3d
+    q = copy.deepcopy(p)
+    q["properties"]["T_0"] *= 0.5
+    q["properties"]["x_0"] *= 2.0
+    oj = orc.OracleJet(q)
+    jm.time = oj.time = 1.0 * con.year
+    assert_parity(jm.emission_measure(), oj.emission_measure(), "EM", rtol=1e-12)
+    f = np.array([5e9, 4.3e10])
+    # the Gaunt factor of the q_T = 0 branch is a scalar of params T_0: evaluate the oracle's
+    # optical depth with the T_0 the GPU model still carries in its parameter dict
+    oj.p["properties"]["T_0"] = p["properties"]["T_0"]
+    assert_parity(jm.optical_depth_ff(f), oj.optical_depth_ff(f), "tau_ff", rtol=1e-12)
+    chans = cases.line_channels(orc.rrl_nu_0('H', 58, 1), 16, 4e5)
+    assert_parity(jm.optical_depth_rrl('H58a', chans), oj.optical_depth_rrl('H58a', chans),
+                  "tau_rrl", floor=1e-290)
+    assert np.array_equal(np.nan_to_num(jm.temperature), np.nan_to_num(0.5 * t3d))
+    with pytest.raises(NotImplementedError):
+        jm.vel = jm.vel
+        jm.emission_measure()
