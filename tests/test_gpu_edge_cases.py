@@ -126,8 +126,10 @@ def test_user_assigned_temperature_and_ion_fraction():
     jm.time = oj.time = 1.0 * con.year
     assert_parity(jm.emission_measure(), oj.emission_measure(), "EM", rtol=1e-12)
     f = np.array([5e9, 4.3e10])
-    # the Gaunt factor of the q_T = 0 branch is a scalar of params T_0: evaluate the oracle's
-    # optical depth with the T_0 the GPU model still carries in its parameter dict
+    # the Gaunt factor of the q_T = 0 branch is a scalar of params T_0 (classes.py:1421-1425),
+    # which a setter does not touch: cache the oracle's halved temperature grid, then give it
+    # the T_0 the GPU model still carries in its parameter dict
+    oj.temperature()
     oj.p["properties"]["T_0"] = p["properties"]["T_0"]
     assert_parity(jm.optical_depth_ff(f), oj.optical_depth_ff(f), "tau_ff", rtol=1e-12)
     chans = cases.line_channels(orc.rrl_nu_0('H', 58, 1), 16, 4e5)
