@@ -247,7 +247,7 @@ def run_gpu(args):
     def device_step():
         """HBM-resident step: fill + fused sweep + epilogue (+ all-gather of tiles)."""
         jm = make_model()
-        jm._ensure_filled()
+        jm._ensure_filled(sync=False)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         jm._pass(line, chans, contsub=False)

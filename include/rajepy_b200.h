@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RJP_ABI_VERSION 4
+#define RJP_ABI_VERSION 5
 #define RJP_MAX_BURSTS 16
 
 enum {
@@ -195,24 +195,27 @@ int rjp_cell_field(const rjp_model* m_host, const rjp_epoch* ep_host,
 int rjp_override_cells(const rjp_model* m_host, const uint8_t* nverts, int32_t field,
                        const double* values, rjp_cell* cells, void* stream);
 
-/* List of the rays whose extent is non-empty (slab-local ray index x_local * nz + z), in
- * arbitrary order: the channel loop launches one CTA per listed ray.  `list` holds up to
- * nray entries, *n_active (device) receives the count.  Call after rjp_fill_grid /
- * rjp_patch_cells. */
-int rjp_ray_list(const int32_t* extents, int64_t nray, int32_t* list, int32_t* n_active,
-                 void* stream);
+/* Ordered list of the rays whose extent is non-empty (slab-local ray index x_local * nz + z,
+ * ASCENDING): the ray kernels pull their work from it.  `list` holds up to nray entries,
+ * `chunk_counts` is scratch of rjp_ray_list_chunks(nray) int32, *n_active (DEVICE) receives the
+ * count and STAYS on the device -- rjp_integrate / rjp_los_means read it there, so the host
+ * never has to wait for it.  Call after rjp_fill_grid / rjp_patch_cells. */
+int rjp_ray_list(const int32_t* extents, int64_t nray, int32_t* list, int32_t* chunk_counts,
+                 int32_t* n_active, void* stream);
+int64_t rjp_ray_list_chunks(int64_t nray);
 
-/* Line-of-sight pass (K3+K4+K5).  The dense sweep reads every cell of the slab once
- * (continuum sums); the channel loop walks only the per-ray in-jet extents recorded by the
- * fill (one CTA per ray of `ray_list`, n_active of them) and runs beside the sweep on
- * `stream2` when one is given (NULL: same stream).
+/* Line-of-sight pass (K3+K4+K5).  The ray kernels walk only the per-ray in-jet extents recorded
+ * by the fill (persistent CTAs pull the rays of `ray_list`; *n_active is read on the device)
+ * and run on `stream2` when one is given (NULL: same stream) beside the constant writer, which
+ * streams the 0 / NaN of the rays that miss the jet with TMA bulk stores on `stream`.
  * Replaces emission_measure (classes.py:1101-1128), optical_depth_ff (:1353-1447),
  * the nanmean temperature of intensity_ff (:1471-1473), optical_depth_rrl (:1130-1229)
  * and intensity_rrl/flux_rrl (:1231-1351).
  *   em, kff, tsum [nxs*nz] double, tcount [nxs*nz] int32 (always written)
- *   extents / ray_list (from rjp_fill_grid / rjp_ray_list): the pass walks only the recorded
- *   in-jet extents of the listed rays and never reads the empty part of the state; with
- *   extents = NULL (continuum-only passes) every cell of the state is swept instead.
+ *   extents / ray_list / n_active (from rjp_fill_grid / rjp_ray_list); with any of them NULL
+ *   (continuum-only passes) every cell of the state is swept instead (dense sweep).
+ *   cursor: DEVICE scratch of 2 int32, zero-initialised by the caller ONCE; the line kernel
+ *   uses it as its ticket counter and leaves it zero again (required for line passes).
  *   line/ch may be NULL/nchan = 0 for a continuum-only pass; otherwise
  *   tau_rrl and/or flux_rrl ([nchan][nxs][nz] double) may each be NULL.
  *   contsub: 0 -> flux_rrl includes S_ff (what Pipeline requests, classes.py:2450).
@@ -223,8 +226,8 @@ int rjp_ray_list(const int32_t* extents, int64_t nray, int32_t* list, int32_t* n
  * On return all work is ordered on `stream` (stream2 is joined back).              */
 int rjp_integrate(const rjp_model* m_host, const rjp_epoch* ep_host,
                   const rjp_continuum* cont_host, const rjp_cell* cells,
-                  const int32_t* extents, const int32_t* ray_list, int32_t n_active,
-                  double* em, double* kff, double* tsum,
+                  const int32_t* extents, const int32_t* ray_list, const int32_t* n_active,
+                  int32_t* cursor, double* em, double* kff, double* tsum,
                   int32_t* tcount, const rjp_line* line_host, const rjp_channels* ch_host,
                   int32_t nchan, int32_t contsub, double* tau_rrl, double* flux_rrl,
                   int64_t cube_plane, int64_t cube_offset, void* stream, void* stream2);
@@ -240,6 +243,9 @@ int rjp_integrate(const rjp_model* m_host, const rjp_epoch* ep_host,
  *                    are left untouched (the caller's own slab when `extents` covers the
  *                    whole image: ONE launch then writes every other slab's constants).
  *                    tau or flux may be NULL.
+ *                    Whole tiles of 1024 consecutive constant rays go out as TMA bulk stores
+ *                    (needs even cube_plane / cube_offset / nray and 16-byte aligned cubes,
+ *                    else predicated scalar stores).
  *                    light != 0: a small grid meant to run on a side stream beside a long
  *                    channel loop; 0: a grid that reaches the HBM write bandwidth alone.
  * ray_ids index into a plane (global ray = x * nz + z for a full-size cube).          */
@@ -267,7 +273,7 @@ int rjp_continuum_images(const double* kff, const double* tsum, const int32_t* t
  *   2 mean ionisation fraction   3 mean (v_los - v_lsr) [km/s]
  *   4 min n, 5 max n, 6 max T along the ray;   NaN where the ray has no finite value.     */
 int rjp_los_means(const rjp_model* m_host, const rjp_epoch* ep_host, const uint8_t* nverts,
-                  const int32_t* extents, const int32_t* ray_list, int32_t n_active,
+                  const int32_t* extents, const int32_t* ray_list, const int32_t* n_active,
                   double* out, void* stream);
 
 /* Voigt profile function of the channel loop, element-wise: out[i] = Re w(x[i] + i y[i]),

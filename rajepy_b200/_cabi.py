@@ -64,7 +64,10 @@ _lib = None
 EXPORTS = ("rjp_strerror", "rjp_last_cuda_error", "rjp_abi_version", "rjp_struct_sizes",
            "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field", "rjp_ray_list", "rjp_integrate",
            "rjp_continuum_images", "rjp_voigt_profile", "rjp_brick_count", "rjp_pack_rays",
-           "rjp_scatter_rays", "rjp_fill_missed", "rjp_los_means", "rjp_override_cells")
+           "rjp_scatter_rays", "rjp_fill_missed", "rjp_los_means", "rjp_override_cells",
+           "rjp_ray_list_chunks")
+
+ABI_VERSION = 5      # RJP_ABI_VERSION of include/rajepy_b200.h this binding was written for
 
 
 def library_path():
@@ -78,9 +81,15 @@ def load():
     if _lib is not None:
         return _lib
     path = library_path()
-    if not os.path.exists(path) or (os.environ.get("RAJEPY_B200_REBUILD") == "1"):
+    stale = False
+    if os.path.exists(path) and not os.environ.get("RAJEPY_B200_LIB"):
         try:
-            _build.build()
+            stale = _build.have_nvcc() and _build.needs_build()
+        except OSError:
+            stale = False
+    if not os.path.exists(path) or stale or (os.environ.get("RAJEPY_B200_REBUILD") == "1"):
+        try:
+            _build.build(force=True)
         except Exception as exc:  # noqa: BLE001
             raise EngineError(f"CUDA library {path} is missing and could not be built: "
                               f"{exc}") from exc
@@ -95,20 +104,26 @@ def load():
     lib.rjp_strerror.argtypes = [C.c_int]
     lib.rjp_last_cuda_error.restype = C.c_char_p
     lib.rjp_abi_version.restype = C.c_int
+    if lib.rjp_abi_version() != ABI_VERSION:
+        raise EngineError(f"ABI mismatch: {path} implements version {lib.rjp_abi_version()}, "
+                          f"this binding expects {ABI_VERSION} (rebuild: python -m "
+                          f"rajepy_b200.build --force)")
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     lib.rjp_struct_sizes.argtypes = [C.POINTER(i32)] * 6
     lib.rjp_fill_grid.argtypes = [C.POINTER(Model), vp, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.rjp_patch_cells.argtypes = [C.POINTER(Model), vp, vp, i32, vp, vp, vp, vp, vp]
-    lib.rjp_los_means.argtypes = [C.POINTER(Model), C.POINTER(Epoch), vp, vp, vp, i32, vp, vp]
+    lib.rjp_los_means.argtypes = [C.POINTER(Model), C.POINTER(Epoch), vp, vp, vp, vp, vp, vp]
     lib.rjp_los_means.restype = C.c_int
     lib.rjp_override_cells.argtypes = [C.POINTER(Model), vp, i32, vp, vp, vp]
     lib.rjp_override_cells.restype = C.c_int
     lib.rjp_brick_count.argtypes = [C.POINTER(Model)]
     lib.rjp_brick_count.restype = i64
     lib.rjp_cell_field.argtypes = [C.POINTER(Model), C.POINTER(Epoch), vp, i32, vp, vp]
-    lib.rjp_ray_list.argtypes = [vp, i64, vp, vp, vp]
+    lib.rjp_ray_list.argtypes = [vp, i64, vp, vp, vp, vp]
+    lib.rjp_ray_list_chunks.argtypes = [i64]
+    lib.rjp_ray_list_chunks.restype = i64
     lib.rjp_integrate.argtypes = [C.POINTER(Model), C.POINTER(Epoch), C.POINTER(Continuum),
-                                  vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(Line),
+                                  vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(Line),
                                   C.POINTER(Channels), i32, i32, vp, vp, i64, i64, vp, vp]
     lib.rjp_pack_rays.argtypes = [vp, i64, vp, i32, i32, i32, vp, vp]
     lib.rjp_scatter_rays.argtypes = [vp, i32, vp, i32, i32, vp, i64, vp]

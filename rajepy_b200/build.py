@@ -26,13 +26,37 @@ def _nvcc():
     return exe
 
 
+def have_nvcc():
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
+def source_hash():
+    """Content hash of everything the library is built from (mtimes do not survive the copy
+    to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "rajepy_b200.h"))
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS + os.environ.get("RAJEPY_B200_NVCC_EXTRA", "").split()).encode())
+    return h.hexdigest()
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps.append(os.path.join(os.path.dirname(HERE), "include", "rajepy_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(LIB + ".hash") as f:
+            return f.read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force=False, verbose=False):
@@ -48,6 +72,8 @@ def build(force=False, verbose=False):
     if res.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed")
+    with open(LIB + ".hash", "wt") as f:
+        f.write(source_hash())
     if verbose:
         print(log)
     return LIB

@@ -14,17 +14,18 @@ int rjp_launch_patch(const rjp_model*, const int64_t*, const uint8_t*, int32_t, 
 int rjp_launch_field(const rjp_model*, const rjp_epoch*, const uint8_t*, int32_t, double*,
                      cudaStream_t);
 int rjp_launch_integrate(const rjp_model*, const rjp_epoch*, const rjp_continuum*,
-                         const rjp_cell*, const int32_t*, const int32_t*, int, double*, double*,
-                         double*, int32_t*, const rjp_line*, const rjp_channels*, int, int,
-                         double, double*, double*, long long, long long, cudaStream_t,
-                         cudaStream_t);
+                         const rjp_cell*, const int32_t*, const int32_t*, const int32_t*,
+                         int32_t*, double*, double*, double*, int32_t*, const rjp_line*,
+                         const rjp_channels*, int, int, double, double*, double*, long long,
+                         long long, cudaStream_t, cudaStream_t);
 int rjp_launch_fill_missed(const int32_t*, long long, int, long long, long long, long long,
                            long long, double*, double*, int, cudaStream_t);
 int rjp_launch_pack_rays(const double*, long long, const int32_t*, int, int, int, double*,
                          cudaStream_t);
 int rjp_launch_scatter_rays(const double*, int, const int32_t*, int, int, double*, long long,
                             cudaStream_t);
-int rjp_launch_ray_list(const int32_t*, int, int32_t*, int32_t*, cudaStream_t);
+int rjp_launch_ray_list(const int32_t*, int, int32_t*, int32_t*, int32_t*, cudaStream_t);
+int rjp_ray_list_chunk(void);
 int rjp_launch_continuum_images(const double*, const double*, const int32_t*, int64_t,
                                 const double*, const double*, double, int, double*, double*,
                                 double*, cudaStream_t);
@@ -32,7 +33,7 @@ int rjp_launch_voigt_profile(const double*, const double*, int64_t, double*, cud
 int rjp_launch_override(const rjp_model*, const uint8_t*, int32_t, const double*, rjp_cell*,
                         cudaStream_t);
 int rjp_launch_los_means(const rjp_model*, const rjp_epoch*, const uint8_t*, const int32_t*,
-                         const int32_t*, int, double*, cudaStream_t);
+                         const int32_t*, const int32_t*, double*, cudaStream_t);
 }
 
 static thread_local char g_cuda_err[256] = "";
@@ -116,16 +117,25 @@ extern "C" int rjp_cell_field(const rjp_model* m, const rjp_epoch* ep, const uin
   return check_launch(rjp_launch_field(m, ep, nverts, field, out, (cudaStream_t)stream));
 }
 
+extern "C" int64_t rjp_ray_list_chunks(int64_t nray) {
+  if (nray < 0) return RJP_ERR_ARG;
+  const int64_t c = rjp_ray_list_chunk();
+  return (nray + c - 1) / c;
+}
+
 extern "C" int rjp_ray_list(const int32_t* extents, int64_t nray, int32_t* list,
-                            int32_t* n_active, void* stream) {
-  if (!extents || !list || !n_active || nray < 0 || nray > 2147483647LL) return RJP_ERR_ARG;
-  return check_launch(rjp_launch_ray_list(extents, (int)nray, list, n_active,
+                            int32_t* chunk_counts, int32_t* n_active, void* stream) {
+  if (!extents || !list || !n_active || nray < 0 || nray > 2147483647LL ||
+      (nray > 0 && !chunk_counts))
+    return RJP_ERR_ARG;
+  return check_launch(rjp_launch_ray_list(extents, (int)nray, list, chunk_counts, n_active,
                                           (cudaStream_t)stream));
 }
 
 extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_continuum* ct,
                              const rjp_cell* cells, const int32_t* extents,
-                             const int32_t* ray_list, int32_t n_active, double* em,
+                             const int32_t* ray_list, const int32_t* n_active,
+                             int32_t* cursor, double* em,
                              double* kff, double* tsum, int32_t* tcount, const rjp_line* ln,
                              const rjp_channels* ch, int32_t nchan, int32_t contsub,
                              double* tau_rrl, double* flux_rrl, int64_t cube_plane,
@@ -139,11 +149,11 @@ extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_
     if (!ln || !ch || !ch->dnu || !ch->nu || !ch->cff || !ch->aff || !ch->bnu)
       return RJP_ERR_ARG;
     if (!tau_rrl && !flux_rrl) return RJP_ERR_ARG;
-    if (!extents || n_active < 0 || (n_active > 0 && !ray_list)) return RJP_ERR_ARG;
+    if (!extents || !ray_list || !n_active || !cursor) return RJP_ERR_ARG;
     if (cube_plane < 0 || cube_offset < 0) return RJP_ERR_ARG;
   }
-  return check_launch(rjp_launch_integrate(m, ep, ct, cells, extents, ray_list, n_active, em,
-                                           kff, tsum, tcount,
+  return check_launch(rjp_launch_integrate(m, ep, ct, cells, extents, ray_list, n_active, cursor,
+                                           em, kff, tsum, tcount,
                                            ln, ch, nchan, contsub, ln ? ln->dn_max : 0.0,
                                            tau_rrl, flux_rrl, cube_plane, cube_offset,
                                            (cudaStream_t)stream, (cudaStream_t)stream2));
@@ -198,10 +208,9 @@ extern "C" int rjp_scatter_rays(const double* in, int32_t n_stride, const int32_
 }
 
 extern "C" int rjp_los_means(const rjp_model* m, const rjp_epoch* ep, const uint8_t* nverts,
-                             const int32_t* extents, const int32_t* ray_list, int32_t n_active,
-                             double* out, void* stream) {
-  if (!model_ok(m) || !ep || !nverts || !extents || !out || n_active < 0 ||
-      (n_active > 0 && !ray_list))
+                             const int32_t* extents, const int32_t* ray_list,
+                             const int32_t* n_active, double* out, void* stream) {
+  if (!model_ok(m) || !ep || !nverts || !extents || !out || !n_active || !ray_list)
     return RJP_ERR_ARG;
   if (ep->n_blue < 0 || ep->n_blue > RJP_MAX_BURSTS || ep->n_red < 0 ||
       ep->n_red > RJP_MAX_BURSTS)

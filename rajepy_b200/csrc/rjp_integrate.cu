@@ -15,14 +15,16 @@
 // walk yields the ray's continuum sums (EM, K, sum T, count) and the flux epilogue.
 //
 // K3 `continuum_rays_kernel` -- continuum-only passes: one warp per jet-crossing ray.
-// `missed_rays_kernel` streams the constants (0 / NaN) of the rays that miss the jet into
-// the images and cubes -- the only HBM-bound part of the pass (write-only), run beside
-// the channel loop on the caller's first stream.
+// `const_tiles_kernel` streams the constants (0 / NaN) of the rays that miss the jet into
+// the images and cubes with TMA bulk stores -- the only HBM-bound part of the pass
+// (write-only), run beside the channel loop on the caller's first stream.
 //
 // `integrate_continuum_kernel` -- the dense sweep for callers that have a cell state but no
 // extents: every 16-byte cell read once, CTA = 32 adjacent rays, lanes along z so every
 // warp-wide load is one contiguous 512-byte row, 8 rows in flight per warp; measured at the
 // HBM copy bandwidth (profiles/README.md).
+#include <stdlib.h>
+#include <mutex>
 #include "rjp_device.cuh"
 
 namespace rjp {
@@ -57,7 +59,7 @@ constexpr int RPW = 8;          // rows in flight per warp
 #ifndef RJP_MINB128
 #define RJP_MINB128 4
 #endif
-constexpr int GCH = RJP_GCH;    // channels per thread of the line kernel
+constexpr int GCH_MAX = RJP_GCH;  // channels per thread of the widest line-kernel variant
 constexpr int LINE_THREADS = 256;
 
 struct LineEntry {   // channel-independent factors of one in-jet cell (rrls.py:329-389)
@@ -319,55 +321,114 @@ __device__ __forceinline__ double planck_factor(const LineEntry& e, double dn) {
 }
 
 // Rays that miss the jet: EM = K = sum T = 0, count = 0, tau_L = 0 and flux = NaN in every
-// channel (nansum / nanmean of an all-NaN column).  Pure streaming writes;
-// rays that cross the jet are left to the ray kernels, so the two can run concurrently.
-__global__ void __maxnreg__(32)
-missed_rays_kernel(const int2* __restrict__ extents, size_t nray, int nchan,
+// channel (nansum / nanmean of an all-NaN column) -- 8 GB of constants at
+// 1024^2 rays x 512 channels x 2 cubes, the only HBM-bound part of the pass.  The ray index
+// space is cut into tiles of CT_TILE consecutive rays (one sky row at nz = 1024).  ~90 % of
+// the tiles contain no jet-crossing ray at all: for those ONE elected thread streams the
+// constant out of shared memory with TMA bulk stores (cp.async.bulk.global.shared::cta, SASS
+// UBLKCP.G.S; 8 KB per instruction, the source tile never changes so nothing waits on the
+// reads) -- practically no issue slots, which is what lets this kernel run beside the
+// issue-bound channel loop.  Tiles that contain jet-crossing rays (or rays of the skip range)
+// take predicated scalar stores; the ray kernels own the jet-crossing columns.
+//   Ray i of `extents` is element offset + i of every cube plane (plane = elements per
+// plane): a slab writes into its rows of a full-size cube this way.  Rays in
+// [skip_lo, skip_hi) are left alone (multi-GPU: the own slab inside the global ray range).
+constexpr int CT_TILE = 1024;    // rays per tile (8 KB of doubles)
+#ifndef RJP_CT_CG
+#define RJP_CT_CG 32             // channel planes per work item
+#endif
+
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(32)
+const_tiles_kernel(const int2* __restrict__ extents, size_t nray, int nchan,
                    double* __restrict__ em, double* __restrict__ kff,
                    double* __restrict__ tsum, int32_t* __restrict__ tcount,
                    double* __restrict__ tau, double* __restrict__ flux, size_t plane,
-                   size_t offset, size_t skip_lo, size_t skip_hi) {
-  // persistent: a warp takes 128 consecutive rays at a time (4 per lane) and loops over the
-  // channel planes -- no loads inside the store stream; a light grid leaves the SMs to the
-  // channel loop.  Ray i of `extents` is element offset + i of every cube plane (plane =
-  // elements per plane): a slab writes into its rows of a full-size cube this way.  Rays in
-  // [skip_lo, skip_hi) are left alone (multi-GPU: the own slab inside the global ray range).
+                   size_t offset, size_t skip_lo, size_t skip_hi, int use_bulk) {
+  __shared__ __align__(128) double s_zero[CT_TILE];
+  __shared__ __align__(128) double s_nan[CT_TILE];
   RJP_STAMP_BEGIN(1)
-  const int lane = threadIdx.x & 31;
-  const size_t gw = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const size_t nw = (size_t)gridDim.x * (blockDim.x >> 5);
+  const int lane = threadIdx.x;
   const double nanv = dnan();
-  for (size_t r0 = gw * 128; r0 < nray; r0 += nw * 128) {
-    bool miss[4];
-    bool any = false;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const size_t ray = r0 + lane + 32 * k;
-      miss[k] = false;
-      if (ray < nray && !(ray >= skip_lo && ray < skip_hi)) {
-        const int2 e = __ldg(extents + ray);
-        miss[k] = e.x >= e.y;
+  for (int i = lane; i < CT_TILE; i += 32) {
+    s_zero[i] = 0.0;
+    s_nan[i] = nanv;
+  }
+  __syncwarp();
+  // make the generic-proxy writes above visible to the async proxy (TMA reads)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const uint32_t a_zero = (uint32_t)__cvta_generic_to_shared(s_zero);
+  const uint32_t a_nan = (uint32_t)__cvta_generic_to_shared(s_nan);
+  const size_t ntiles = (nray + CT_TILE - 1) / CT_TILE;
+  const int ncg = nchan > 0 ? (nchan + RJP_CT_CG - 1) / RJP_CT_CG : 1;
+  const size_t nitems = ntiles * (size_t)ncg;
+  // item = tile * ncg + channel group; consecutive items go to different CTAs
+  for (size_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const size_t t = item / ncg;
+    const int cg = (int)(item - t * ncg);
+    const size_t r0 = t * CT_TILE;
+    // bit i of `miss`: ray r0 + 32 i + lane misses the jet (and is not in the skip range);
+    // bit i of `valid`: that ray exists
+    unsigned miss = 0u, valid = 0u;
+#pragma unroll 8
+    for (int i = 0; i < CT_TILE / 32; ++i) {
+      const size_t ray = r0 + 32 * i + lane;
+      if (ray < nray) {
+        valid |= 1u << i;
+        if (!(ray >= skip_lo && ray < skip_hi)) {
+          const int2 e = __ldg(extents + ray);
+          if (e.x >= e.y) miss |= 1u << i;
+        }
       }
-      if (miss[k] && em != nullptr) {
-        em[ray] = 0.0;
-        kff[ray] = 0.0;
-        tsum[ray] = 0.0;
-        tcount[ray] = 0;
-      }
-      any = any || miss[k];
     }
-    if (!any) continue;
-    for (int c = 0; c < nchan; ++c) {
-      const size_t o = (size_t)c * plane + offset + r0 + lane;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (miss[k]) {
-          if (tau) tau[o + 32 * k] = 0.0;
-          if (flux) flux[o + 32 * k] = nanv;
+    if (cg == 0 && em != nullptr) {     // the four sky images, once per tile
+#pragma unroll 4
+      for (int i = 0; i < CT_TILE / 32; ++i) {
+        if (miss >> i & 1u) {
+          const size_t ray = r0 + 32 * i + lane;
+          em[ray] = 0.0;
+          kff[ray] = 0.0;
+          tsum[ray] = 0.0;
+          tcount[ray] = 0;
+        }
+      }
+    }
+    if (nchan <= 0) continue;
+    const int c_lo = cg * RJP_CT_CG;
+    const int c_hi = (c_lo + RJP_CT_CG < nchan) ? c_lo + RJP_CT_CG : nchan;
+    const size_t n_in = (nray - r0 < (size_t)CT_TILE) ? nray - r0 : (size_t)CT_TILE;
+    // whole tile constant?  (a short last tile counts if all of its rays miss and its
+    // byte count is a multiple of 16)
+    const bool all_const = __all_sync(0xffffffffu, miss == valid) && (n_in & 1) == 0;
+    if (all_const && use_bulk) {
+      if (lane == 0) {
+        const uint32_t bytes = (uint32_t)(n_in * sizeof(double));
+        for (int c = c_lo; c < c_hi; ++c) {
+          const size_t o = (size_t)c * plane + offset + r0;
+          if (tau) bulk_store(tau + o, a_zero, bytes);
+          if (flux) bulk_store(flux + o, a_nan, bytes);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else if (__any_sync(0xffffffffu, miss != 0u)) {
+      for (int c = c_lo; c < c_hi; ++c) {
+        const size_t o = (size_t)c * plane + offset + r0 + lane;
+#pragma unroll 8
+        for (int i = 0; i < CT_TILE / 32; ++i) {
+          if (miss >> i & 1u) {
+            if (tau) tau[o + 32 * i] = 0.0;
+            if (flux) flux[o + 32 * i] = nanv;
+          }
         }
       }
     }
   }
+  // the shared-memory source must outlive the reads, the writes must have landed at exit
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   RJP_STAMP_END(1)
 }
 
@@ -396,73 +457,139 @@ __global__ void scatter_rays_kernel(const double* __restrict__ in, int n_stride,
   }
 }
 
-// Continuum-only walk: one warp per jet-crossing ray, lanes stride along the extent.
+// Continuum-only walk: one warp per jet-crossing ray, lanes stride along the extent.  The
+// number of listed rays is read on the device (the host never waits for it); warps stride
+// over the list.
 __global__ void __launch_bounds__(256)
 continuum_rays_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
                       const double2* __restrict__ cells, const int2* __restrict__ extents,
-                      const int32_t* __restrict__ ray_list, const int n_active,
+                      const int32_t* __restrict__ ray_list,
+                      const int32_t* __restrict__ n_active_dev,
                       double* __restrict__ em, double* __restrict__ kff,
                       double* __restrict__ tsum, int32_t* __restrict__ tcount) {
   __shared__ Params s_p;
   stage_params(&s_p, m, ep);
   const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (w >= n_active) return;
-  const int ray = ray_list[w];
-  const int xl = ray / m.nz, iz = ray - xl * m.nz;
-  const int ix = m.x_lo + xl;
-  const int2 ext = extents[ray];
-  const Ray rc = ray_of(s_p.m, ix, iz);
-  const double2* col = cells + (size_t)xl * m.ny * m.nz + iz;
-  ContAcc a = {0.0, 0.0, 0.0, 0};
-  for (int iy = ext.x + lane; iy < ext.y; iy += 32) {
-    const double2 c = col[(size_t)iy * m.nz];
-    if (empty_cell(c)) continue;
-    accumulate(a, decode(c, s_p, rc, ix, iy, iz), ct.t_exponent);
-  }
+  const int n_active = *n_active_dev;
+  const int nw = gridDim.x * (blockDim.x >> 5);
+  for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_active; w += nw) {
+    const int ray = ray_list[w];
+    const int xl = ray / m.nz, iz = ray - xl * m.nz;
+    const int ix = m.x_lo + xl;
+    const int2 ext = extents[ray];
+    const Ray rc = ray_of(s_p.m, ix, iz);
+    const double2* col = cells + (size_t)xl * m.ny * m.nz + iz;
+    ContAcc a = {0.0, 0.0, 0.0, 0};
+    for (int iy = ext.x + lane; iy < ext.y; iy += 32) {
+      const double2 c = col[(size_t)iy * m.nz];
+      if (empty_cell(c)) continue;
+      accumulate(a, decode(c, s_p, rc, ix, iy, iz), ct.t_exponent);
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a.em += __shfl_xor_sync(0xffffffffu, a.em, o);
-    a.kff += __shfl_xor_sync(0xffffffffu, a.kff, o);
-    a.tsum += __shfl_xor_sync(0xffffffffu, a.tsum, o);
-    a.cnt += __shfl_xor_sync(0xffffffffu, a.cnt, o);
-  }
-  if (lane == 0) {
-    em[ray] = a.em * ct.em_scale;
-    kff[ray] = a.kff * ct.tau_scale;
-    tsum[ray] = a.tsum;
-    tcount[ray] = a.cnt;
+    for (int o = 16; o > 0; o >>= 1) {
+      a.em += __shfl_xor_sync(0xffffffffu, a.em, o);
+      a.kff += __shfl_xor_sync(0xffffffffu, a.kff, o);
+      a.tsum += __shfl_xor_sync(0xffffffffu, a.tsum, o);
+      a.cnt += __shfl_xor_sync(0xffffffffu, a.cnt, o);
+    }
+    if (lane == 0) {
+      em[ray] = a.em * ct.em_scale;
+      kff[ray] = a.kff * ct.tau_scale;
+      tsum[ray] = a.tsum;
+      tcount[ray] = a.cnt;
+    }
   }
 }
 
-__global__ void ray_list_kernel(const int2* __restrict__ extents, int nray,
-                                int32_t* __restrict__ list, int32_t* __restrict__ n_active) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool on = false;
-  if (i < nray) {
-    const int2 e = extents[i];
-    on = e.x < e.y;
+// Ordered compaction of the jet-crossing rays (extent non-empty) in two small launches:
+// per-chunk counts, then every chunk re-derives its flags, adds the counts of the chunks
+// before it and writes its rays in ascending order -- neighbouring CTAs of the ray kernels
+// then write neighbouring cube columns, the sparse exchanges pack / scatter coalesced, and no
+// sort is needed.  *n_active stays on the device: the ray kernels read it there.
+constexpr int RL_CHUNK = 1024, RL_THREADS = 256;
+
+__device__ __forceinline__ int block_sum_256(int v, int* s_w /* [8] */) {
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) s_w[wrp] = v;
+  __syncthreads();
+  int t = 0;
+#pragma unroll
+  for (int w = 0; w < RL_THREADS / 32; ++w) t += s_w[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(RL_THREADS)
+ray_count_kernel(const int2* __restrict__ extents, int nray, int32_t* __restrict__ counts) {
+  __shared__ int s_w[RL_THREADS / 32];
+  const int base = blockIdx.x * RL_CHUNK;
+  int n = 0;
+#pragma unroll
+  for (int k = 0; k < RL_CHUNK / RL_THREADS; ++k) {
+    const int i = base + k * RL_THREADS + threadIdx.x;
+    if (i < nray) {
+      const int2 e = extents[i];
+      n += e.x < e.y;
+    }
   }
-  // warp-aggregated append
-  const unsigned m = __ballot_sync(0xffffffffu, on);
-  if (m == 0u) return;
-  const int lane = threadIdx.x & 31;
-  int base = 0;
-  if (lane == __ffs(m) - 1) base = atomicAdd(n_active, __popc(m));
-  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-  if (on) list[base + __popc(m & ((1u << lane) - 1u))] = i;
+  n = block_sum_256(n, s_w);
+  if (threadIdx.x == 0) counts[blockIdx.x] = n;
+}
+
+__global__ void __launch_bounds__(RL_THREADS)
+ray_compact_kernel(const int2* __restrict__ extents, int nray,
+                   const int32_t* __restrict__ counts, int32_t* __restrict__ list,
+                   int32_t* __restrict__ n_active) {
+  __shared__ int s_w[RL_THREADS / 32];
+  __shared__ int s_run[RL_THREADS / 32];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  // rays listed by the chunks before this one (the last chunk also publishes the total)
+  int before = 0;
+  for (int c = threadIdx.x; c < (int)blockIdx.x; c += RL_THREADS) before += counts[c];
+  before = block_sum_256(before, s_w);
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_active = before + counts[blockIdx.x];
+  const int base = blockIdx.x * RL_CHUNK;
+  for (int k = 0; k < RL_CHUNK / RL_THREADS; ++k) {
+    const int i = base + k * RL_THREADS + threadIdx.x;
+    bool on = false;
+    if (i < nray) {
+      const int2 e = extents[i];
+      on = e.x < e.y;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, on);
+    __syncthreads();
+    if (lane == 0) s_run[wrp] = __popc(bal);
+    __syncthreads();
+    int off = before, tot = 0;
+#pragma unroll
+    for (int w = 0; w < RL_THREADS / 32; ++w) {
+      if (w < wrp) off += s_run[w];
+      tot += s_run[w];
+    }
+    if (on) list[off + __popc(bal & ((1u << lane) - 1u))] = i;
+    before += tot;
+  }
 }
 
 // UNI: the channels are equally spaced (rjp_line.chan_step != 0): the channel offsets are
 // formed on the fly from two per-thread scalars instead of living in 24 registers (16 of
 // which spilled), which is what lets the kernel fit more warps per SM.
-template <int MAXT, int MINB, bool UNI>
+// GCH = channels per thread (8 for whole cubes; 4 / 2 when a rank of a channel-sharded run
+// owns only 128 / 64 channels, so that a one-warp CTA still covers them without idle slots).
+// Persistent: the CTAs pull rays from the list with a ticket counter (`cursor`, two ints that
+// the last CTA to leave resets to zero) and read the list length on the device, so the host
+// never has to know how many rays cross the jet.
+template <int MAXT, int MINB, bool UNI, int GCH>
 __global__ void __launch_bounds__(MAXT, MINB)
 integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
                       const rjp_line ln, const rjp_channels ch, const int nchan,
                       const int c_first, const int contsub, const double dn_max,
                       const double2* __restrict__ cells, const int2* __restrict__ extents,
-                      const int32_t* __restrict__ ray_list, double* __restrict__ em,
+                      const int32_t* __restrict__ ray_list,
+                      const int32_t* __restrict__ n_active_dev, int32_t* __restrict__ cursor,
+                      double* __restrict__ em,
                       double* __restrict__ kff, double* __restrict__ tsum,
                       int32_t* __restrict__ tcount, double* __restrict__ tau_rrl,
                       double* __restrict__ flux_rrl, const size_t plane,
@@ -476,6 +603,7 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   __shared__ double s_part[3][MAXT];
   __shared__ int s_pcnt[MAXT];
   __shared__ int s_woff[2][MAXT / 32 + 1];
+  __shared__ int s_ticket;
   static_assert(sizeof(LineEntry) == sizeof(FastEntry), "shared batch buffer");
   RJP_STAMP_BEGIN(0)
   stage_params(&s_p, m, ep);
@@ -487,10 +615,7 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   asm volatile("" : "+r"(tab));  // keep it in a register (rematerialising costs S2R + LEA)
   const int NT = blockDim.x;
   const int g = threadIdx.x, lane = g & 31, wrp = g >> 5, nwarps = NT >> 5;
-  const int ray = ray_list[blockIdx.x];          // slab-local ray index = xl * nz + iz
-  const int xl = ray / m.nz, iz = ray - xl * m.nz;
-  const int ix = m.x_lo + xl;
-  const int2 ext = extents[ray];
+  const int n_active = *n_active_dev;
 
   // thread g owns channels g, g + NT, g + 2 NT, ...: at every step the lanes of a warp hold
   // 32 neighbouring channels, i.e. nearly the same point of the line profile, so the
@@ -511,13 +636,22 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
 #pragma unroll
     for (int j = 0; j < GCH; j += 2) dnf2[j >> 1] = pk2((float)dn[j], (float)dn[j + 1]);
   }
+
+  for (;;) {                                         // one jet-crossing ray per iteration
+  if (g == 0) s_ticket = atomicAdd(cursor, 1);
+  __syncthreads();
+  const int ticket = s_ticket;
+  if (ticket >= n_active) break;
+  const int ray = ray_list[ticket];                // slab-local ray index = xl * nz + iz
+  const int xl = ray / m.nz, iz = ray - xl * m.nz;
+  const int ix = m.x_lo + xl;
+  const int2 ext = extents[ray];
   double acc[GCH];
 #pragma unroll
   for (int j = 0; j < GCH; ++j) acc[j] = 0.0;
   ContAcc ca = {0.0, 0.0, 0.0, 0};
   const Ray rc = ray_of(s_p.m, ix, iz);
   const double2* col = cells + (size_t)xl * m.ny * m.nz + iz;
-  __syncthreads();
 
   for (int y0 = ext.x; y0 < ext.y; y0 += NT) {
     // phase 1: every thread prepares one cell of the extent; cells that emit no line are
@@ -686,6 +820,15 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
       flux_rrl[(size_t)c * plane + cube_offset + ray] = s;
     }
   }
+  }  // ray loop
+  // the last CTA to leave re-arms the ticket counter for the next launch
+  if (g == 0) {
+    __threadfence();
+    if (atomicAdd(cursor + 1, 1) == (int)gridDim.x - 1) {
+      cursor[0] = 0;
+      cursor[1] = 0;
+    }
+  }
   RJP_STAMP_END(0)
 }
 
@@ -698,12 +841,14 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
 __global__ void __launch_bounds__(256)
 los_means_kernel(const rjp_model m, const rjp_epoch ep, const uint8_t* __restrict__ nverts,
                  const int2* __restrict__ extents, const int32_t* __restrict__ ray_list,
-                 const int n_active, const size_t nray, double* __restrict__ out) {
+                 const int32_t* __restrict__ n_active_dev, const size_t nray,
+                 double* __restrict__ out) {
   __shared__ Params s_p;
   stage_params(&s_p, m, ep);
   const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (w >= n_active) return;
+  const int n_active = *n_active_dev;
+  const int nw = gridDim.x * (blockDim.x >> 5);
+  for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_active; w += nw) {
   const int ray = ray_list[w];
   const int xl = ray / m.nz, iz = ray - xl * m.nz;
   const int ix = m.x_lo + xl;
@@ -751,6 +896,7 @@ los_means_kernel(const rjp_model m, const rjp_epoch ep, const uint8_t* __restric
     out[5 * nray + ray] = cnt[0] > 0 ? nmax : dnan();
     out[6 * nray + ray] = cnt[1] > 0 ? tmax : dnan();
   }
+  }
 }
 
 // Diagnostic: Re w(x + iy) with the channel loop's own device routines
@@ -796,53 +942,119 @@ __global__ void continuum_images_kernel(const double* __restrict__ kff,
 using namespace rjp;
 
 extern "C" int rjp_launch_ray_list(const int32_t* extents, int nray, int32_t* list,
-                                   int32_t* n_active, cudaStream_t stream) {
-  if (nray <= 0) return RJP_OK;
-  cudaMemsetAsync(n_active, 0, sizeof(int32_t), stream);
-  ray_list_kernel<<<(nray + 255) / 256, 256, 0, stream>>>(
-      reinterpret_cast<const int2*>(extents), nray, list, n_active);
+                                   int32_t* chunk_counts, int32_t* n_active,
+                                   cudaStream_t stream) {
+  if (nray <= 0) {
+    cudaMemsetAsync(n_active, 0, sizeof(int32_t), stream);
+    return RJP_OK;
+  }
+  const int chunks = (nray + RL_CHUNK - 1) / RL_CHUNK;
+  ray_count_kernel<<<chunks, RL_THREADS, 0, stream>>>(reinterpret_cast<const int2*>(extents),
+                                                      nray, chunk_counts);
+  ray_compact_kernel<<<chunks, RL_THREADS, 0, stream>>>(reinterpret_cast<const int2*>(extents),
+                                                        nray, chunk_counts, list, n_active);
   return RJP_OK;
+}
+
+extern "C" int rjp_ray_list_chunk(void) { return RL_CHUNK; }
+
+// ---------------------------------------------------------------- launch plumbing
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+struct DeviceInfo { int sms; bool carved; };
+
+// Per-device facts and one-off function attributes, guarded for host threads that drive
+// different devices at the same time.
+static DeviceInfo& device_info() {
+  static std::mutex mu;
+  static DeviceInfo info[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DeviceInfo& d = info[dev & 63];
+  std::lock_guard<std::mutex> lock(mu);
+  if (d.sms == 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+    d.sms = sms;
+  }
+  return d;
+}
+
+template <int T, int B, bool U, int G>
+static void carve_line(int pct) {
+  cudaFuncSetAttribute(integrate_line_kernel<T, B, U, G>,
+                       cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
 // Same shared-memory carve-out for the kernels that are meant to be co-resident: an SM only
 // switches its L1 / shared split when it is idle, so a kernel that asks for a different split
 // waits until the other one has drained (measured: the channel loop started 0.9 ms late
-// behind the constant writer, which uses no shared memory).
+// behind a constant writer with a different split).
 static void set_carveouts() {
-  static bool done_on[64] = {};   // function attributes are per device
+  static std::mutex mu;
+  DeviceInfo& d = device_info();
+  std::lock_guard<std::mutex> lock(mu);
+  if (d.carved) return;
+  const int pct = 75;
+  cudaFuncSetAttribute(const_tiles_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(continuum_rays_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  carve_line<32, 16, true, 2>(pct);
+  carve_line<32, 16, true, 4>(pct);
+  carve_line<32, 16, true, 8>(pct);
+  carve_line<64, RJP_MINB64U, true, GCH_MAX>(pct);
+  carve_line<128, RJP_MINB128, true, GCH_MAX>(pct);
+  carve_line<LINE_THREADS, 2, true, GCH_MAX>(pct);
+  carve_line<64, RJP_MINB64, false, GCH_MAX>(pct);
+  carve_line<128, RJP_MINB128, false, GCH_MAX>(pct);
+  carve_line<LINE_THREADS, 2, false, GCH_MAX>(pct);
+  d.carved = true;
+}
+
+// fork / join events of the two-stream pass, created once per (host thread, device)
+static int pass_events(cudaEvent_t* fork, cudaEvent_t* join) {
+  thread_local cudaEvent_t ev[64][2] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  bool& done = done_on[dev & 63];
-  if (done) return;
-  const int pct = 75;
-  cudaFuncSetAttribute(missed_rays_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-  cudaFuncSetAttribute(continuum_rays_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-  const auto attr = cudaFuncAttributePreferredSharedMemoryCarveout;
-  cudaFuncSetAttribute(integrate_line_kernel<64, RJP_MINB64U, true>, attr, pct);
-  cudaFuncSetAttribute(integrate_line_kernel<128, RJP_MINB128, true>, attr, pct);
-  cudaFuncSetAttribute(integrate_line_kernel<LINE_THREADS, 2, true>, attr, pct);
-  cudaFuncSetAttribute(integrate_line_kernel<64, RJP_MINB64, false>, attr, pct);
-  cudaFuncSetAttribute(integrate_line_kernel<128, RJP_MINB128, false>, attr, pct);
-  cudaFuncSetAttribute(integrate_line_kernel<LINE_THREADS, 2, false>, attr, pct);
-  done = true;
+  cudaEvent_t* e = ev[dev & 63];
+  for (int i = 0; i < 2; ++i)
+    if (e[i] == nullptr &&
+        cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming) != cudaSuccess)
+      return RJP_ERR_CUDA;
+  *fork = e[0];
+  *join = e[1];
+  return RJP_OK;
+}
+
+// bulk stores need 16-byte aligned global addresses and sizes
+static bool bulk_ok(const double* tau, const double* flux, size_t plane, size_t offset,
+                    size_t nray) {
+  if (env_int("RJP_NO_BULK", 0)) return false;
+  return (plane % 2 == 0) && (offset % 2 == 0) && (nray % 2 == 0) &&
+         (reinterpret_cast<uintptr_t>(tau) % 16 == 0) &&
+         (reinterpret_cast<uintptr_t>(flux) % 16 == 0);
 }
 
 extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
                                     const rjp_continuum* ct, const rjp_cell* cells,
                                     const int32_t* extents, const int32_t* ray_list,
-                                    int n_active, double* em, double* kff, double* tsum,
-                                    int32_t* tcount, const rjp_line* ln,
-                                    const rjp_channels* ch, int nchan, int contsub,
-                                    double dn_max, double* tau_rrl, double* flux_rrl,
-                                    long long cube_plane, long long cube_offset,
-                                    cudaStream_t stream, cudaStream_t stream2) {
+                                    const int32_t* n_active, int32_t* cursor, double* em,
+                                    double* kff, double* tsum, int32_t* tcount,
+                                    const rjp_line* ln, const rjp_channels* ch, int nchan,
+                                    int contsub, double dn_max, double* tau_rrl,
+                                    double* flux_rrl, long long cube_plane,
+                                    long long cube_offset, cudaStream_t stream,
+                                    cudaStream_t stream2) {
   const int nxs = m->x_hi - m->x_lo;
   const long long ctas = (long long)nxs * ((m->nz + ZT - 1) / ZT);
   if (ctas <= 0 || ctas > 2147483647LL) return RJP_ERR_ARG;
   const double2* c4 = reinterpret_cast<const double2*>(cells);
   const int2* ex2 = reinterpret_cast<const int2*>(extents);
   const bool lines = nchan > 0 && ln != nullptr;
-  if (extents == nullptr || (n_active > 0 && ray_list == nullptr)) {
+  if (extents == nullptr || ray_list == nullptr || n_active == nullptr) {
     // no extents: dense sweep over the whole state (continuum only; the API demands extents
     // for line passes)
     if (lines) return RJP_ERR_ARG;
@@ -854,31 +1066,37 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
   const size_t plane = cube_plane > 0 ? (size_t)cube_plane : nray;
   const size_t coff = cube_plane > 0 ? (size_t)cube_offset : 0;
   if (plane < coff + nray) return RJP_ERR_ARG;
+  if (lines && cursor == nullptr) return RJP_ERR_ARG;
   set_carveouts();
+  const int sms = device_info().sms;
   cudaEvent_t fork = nullptr, join = nullptr;
   cudaStream_t ls = stream;
-  if (n_active > 0 && stream2 != nullptr && stream2 != stream) {
+  if (stream2 != nullptr && stream2 != stream) {
     // fork (before the constant fill is queued): the issue-bound ray walk on stream2 runs
     // beside the write-bound constant fill on stream
-    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess)
+    if (pass_events(&fork, &join) != RJP_OK) return RJP_ERR_CUDA;
+    if (cudaEventRecord(fork, stream) != cudaSuccess ||
+        cudaStreamWaitEvent(stream2, fork, 0) != cudaSuccess)
       return RJP_ERR_CUDA;
-    cudaEventRecord(fork, stream);
-    cudaStreamWaitEvent(stream2, fork, 0);
     ls = stream2;
   }
-  // constants of the rays that miss the jet: a light persistent grid (one 2-warp CTA on
-  // every other SM keeps 3.4 TB/s of stores in flight), launched first so that it is
-  // resident beside the ray kernels; measured best of 74..1184 CTAs x 32..256 threads
-  missed_rays_kernel<<<74, 64, 0, stream>>>(ex2, nray, lines ? nchan : 0, em, kff, tsum, tcount,
-                                            tau_rrl, flux_rrl, plane, coff, 0, 0);
-  if (lines && n_active > 0) {
+  // constants of the rays that miss the jet: one warp per SM streams whole constant tiles
+  // with TMA bulk stores; launched first so that it is resident beside the ray kernels
+  {
+    const int per_sm = env_int("RJP_WRITER_PER_SM", lines ? 1 : 2);
+    const size_t ntiles = (nray + CT_TILE - 1) / CT_TILE;
+    const size_t items = ntiles * (size_t)(lines ? (nchan + RJP_CT_CG - 1) / RJP_CT_CG : 1);
+    size_t grid = (size_t)sms * per_sm;
+    if (grid > items) grid = items;
+    const_tiles_kernel<<<(unsigned)grid, 32, 0, stream>>>(
+        ex2, nray, lines ? nchan : 0, em, kff, tsum, tcount, tau_rrl, flux_rrl, plane, coff, 0, 0,
+        bulk_ok(tau_rrl, flux_rrl, plane, coff, nray) ? 1 : 0);
+  }
+  if (lines) {
     // channel blocks of at most 8 * 256 channels per launch; the first one also writes the
     // continuum images of its rays
-    for (int c0 = 0; c0 < nchan; c0 += GCH * LINE_THREADS) {
-      const int nc = (nchan - c0 < GCH * LINE_THREADS) ? nchan - c0 : GCH * LINE_THREADS;
-      const int groups = (nc + GCH - 1) / GCH;
-      const int threads = ((groups + 31) / 32) * 32;
+    for (int c0 = 0; c0 < nchan; c0 += GCH_MAX * LINE_THREADS) {
+      const int nc = (nchan - c0 < GCH_MAX * LINE_THREADS) ? nchan - c0 : GCH_MAX * LINE_THREADS;
       rjp_channels cb = *ch;
       cb.dnu += c0; cb.nu += c0; cb.cff += c0; cb.aff += c0; cb.bnu += c0;
       const size_t off = (size_t)c0 * plane;
@@ -887,31 +1105,53 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
       double* em_o = (c0 == 0) ? em : nullptr;
       // equally spaced channels (the normal case) take the register-lean instantiation
       const bool uni = ln->chan_step != 0.0;
-#define RJP_LAUNCH_LINE(T, B, U)                                                              \
-  integrate_line_kernel<T, B, U><<<(unsigned)n_active, threads, 0, ls>>>(                     \
-      *m, *ep, *ct, *ln, cb, nc, c0, contsub, dn_max, c4, ex2, ray_list, em_o, kff, tsum, tcount, \
-      t_out, f_out, plane, coff)
-      if (threads <= 64) {
-        if (uni) RJP_LAUNCH_LINE(64, RJP_MINB64U, true);
-        else RJP_LAUNCH_LINE(64, RJP_MINB64, false);
-      } else if (threads <= 128) {
-        if (uni) RJP_LAUNCH_LINE(128, RJP_MINB128, true);
-        else RJP_LAUNCH_LINE(128, RJP_MINB128, false);
+      // threads x channels-per-thread: few channels (a rank of a channel-sharded run) take a
+      // one-warp CTA with 2 / 4 / 8 channels per thread
+      int threads, gch = GCH_MAX;
+      if (uni && nc <= 32 * GCH_MAX) {
+        threads = 32;
+        gch = nc <= 64 ? 2 : (nc <= 128 ? 4 : 8);
+        if (GCH_MAX != 8) gch = GCH_MAX;
       } else {
-        if (uni) RJP_LAUNCH_LINE(LINE_THREADS, 2, true);
-        else RJP_LAUNCH_LINE(LINE_THREADS, 2, false);
+        const int groups = (nc + GCH_MAX - 1) / GCH_MAX;
+        threads = ((groups + 31) / 32) * 32;
+      }
+      const int force_t = env_int("RJP_LINE_THREADS", 0);
+      if (force_t > 0 && uni && force_t * GCH_MAX >= nc) { threads = force_t; gch = GCH_MAX; }
+#define RJP_LAUNCH_LINE(T, B, U, G)                                                           \
+  do {                                                                                        \
+    size_t grid_ = (size_t)sms * (B);                                                         \
+    if (grid_ > nray) grid_ = nray;                                                           \
+    integrate_line_kernel<T, B, U, G><<<(unsigned)grid_, threads, 0, ls>>>(                   \
+        *m, *ep, *ct, *ln, cb, nc, c0, contsub, dn_max, c4, ex2, ray_list, n_active, cursor,  \
+        em_o, kff, tsum, tcount, t_out, f_out, plane, coff);                                  \
+  } while (0)
+      if (threads <= 32 && uni) {
+        if (gch == 2) RJP_LAUNCH_LINE(32, 16, true, 2);
+        else if (gch == 4) RJP_LAUNCH_LINE(32, 16, true, 4);
+        else RJP_LAUNCH_LINE(32, 16, true, 8);
+      } else if (threads <= 64) {
+        if (uni) RJP_LAUNCH_LINE(64, RJP_MINB64U, true, GCH_MAX);
+        else RJP_LAUNCH_LINE(64, RJP_MINB64, false, GCH_MAX);
+      } else if (threads <= 128) {
+        if (uni) RJP_LAUNCH_LINE(128, RJP_MINB128, true, GCH_MAX);
+        else RJP_LAUNCH_LINE(128, RJP_MINB128, false, GCH_MAX);
+      } else {
+        if (uni) RJP_LAUNCH_LINE(LINE_THREADS, 2, true, GCH_MAX);
+        else RJP_LAUNCH_LINE(LINE_THREADS, 2, false, GCH_MAX);
       }
 #undef RJP_LAUNCH_LINE
     }
-  } else if (n_active > 0) {
-    continuum_rays_kernel<<<(n_active + 7) / 8, 256, 0, ls>>>(*m, *ep, *ct, c4, ex2, ray_list,
-                                                                 n_active, em, kff, tsum, tcount);
+  } else {
+    size_t grid = (nray + 7) / 8;
+    if (grid > (size_t)sms * 8) grid = (size_t)sms * 8;
+    continuum_rays_kernel<<<(unsigned)grid, 256, 0, ls>>>(*m, *ep, *ct, c4, ex2, ray_list,
+                                                          n_active, em, kff, tsum, tcount);
   }
   if (fork) {
-    cudaEventRecord(join, stream2);
-    cudaStreamWaitEvent(stream, join, 0);
-    cudaEventDestroy(fork);
-    cudaEventDestroy(join);
+    if (cudaEventRecord(join, stream2) != cudaSuccess ||
+        cudaStreamWaitEvent(stream, join, 0) != cudaSuccess)
+      return RJP_ERR_CUDA;
   }
   return RJP_OK;
 }
@@ -932,11 +1172,17 @@ extern "C" int rjp_launch_fill_missed(const int32_t* extents, long long nray, in
                                       cudaStream_t stream) {
   if (nray <= 0 || nchan <= 0) return RJP_OK;
   set_carveouts();
+  const int sms = device_info().sms;
   // light grid: meant to run on a side stream beside a long channel loop (multi-GPU: the
-  // constants of the OTHER slabs' rays); otherwise a grid that reaches the HBM write peak
-  missed_rays_kernel<<<light ? 148 : 148 * 4, light ? 64 : 128, 0, stream>>>(
+  // constants of the OTHER slabs' rays); otherwise enough warps to reach the HBM write peak
+  const size_t ntiles = ((size_t)nray + CT_TILE - 1) / CT_TILE;
+  const size_t items = ntiles * (size_t)((nchan + RJP_CT_CG - 1) / RJP_CT_CG);
+  size_t grid = (size_t)sms * (light ? 1 : env_int("RJP_WRITER_PER_SM_ALONE", 4));
+  if (grid > items) grid = items;
+  const_tiles_kernel<<<(unsigned)grid, 32, 0, stream>>>(
       reinterpret_cast<const int2*>(extents), (size_t)nray, nchan, nullptr, nullptr, nullptr,
-      nullptr, tau, flux, (size_t)plane, (size_t)offset, (size_t)skip_lo, (size_t)skip_hi);
+      nullptr, tau, flux, (size_t)plane, (size_t)offset, (size_t)skip_lo, (size_t)skip_hi,
+      bulk_ok(tau, flux, (size_t)plane, (size_t)offset, (size_t)nray) ? 1 : 0);
   return RJP_OK;
 }
 
@@ -960,13 +1206,13 @@ extern "C" int rjp_launch_scatter_rays(const double* in, int n_stride, const int
 
 extern "C" int rjp_launch_los_means(const rjp_model* m, const rjp_epoch* ep, const uint8_t* nverts,
                                     const int32_t* extents, const int32_t* ray_list,
-                                    int n_active, double* out, cudaStream_t stream) {
+                                    const int32_t* n_active, double* out, cudaStream_t stream) {
   const size_t nray = (size_t)(m->x_hi - m->x_lo) * m->nz;
   // NaN everywhere (all-ones bytes are a quiet NaN), then the jet-crossing rays
   cudaMemsetAsync(out, 0xFF, sizeof(double) * 7 * nray, stream);
-  if (n_active > 0)
-    los_means_kernel<<<(n_active + 7) / 8, 256, 0, stream>>>(
-        *m, *ep, nverts, reinterpret_cast<const int2*>(extents), ray_list, n_active, nray, out);
+  const size_t want = (nray + 7) / 8;
+  los_means_kernel<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, stream>>>(
+      *m, *ep, nverts, reinterpret_cast<const int2*>(extents), ray_list, n_active, nray, out);
   return RJP_OK;
 }
 

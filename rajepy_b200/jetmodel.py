@@ -28,6 +28,7 @@ from . import logger
 from .sharding import balanced_bounds, even_bounds, gather_x
 
 _TIE_CAPACITY = 1 << 16
+_TIE_ASYNC = 2048         # ties read back with the asynchronous report (the rest on demand)
 
 # number of kernel launches issued through the C ABI by this process (bench.py reports it)
 LAUNCHES = {"count": 0}
@@ -54,24 +55,38 @@ _TIE_DECISIONS = {}     # host re-decisions of near-tie vertices per (geometry, 
 _CONT_COEFFS = {}       # per-frequency continuum coefficients on the device
 
 
-def _take_state(torch, dev, ncell, nbricks):
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), ncell, nbricks)
+def _dev_index(torch, dev):
+    return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
+def _take_state(torch, dev, nxs, ny, nz, nbricks):
+    """Recycled (nverts, cells, brick map) of a slab with exactly this layout, else fresh
+    zero-filled buffers.  The flat cell index and the brick id both depend on (ny, nz), so
+    the key is the layout, not the cell count."""
+    key = (_dev_index(torch, dev), nxs, ny, nz)
     hit = _STATE_POOL.pop(key, None)
-    if hit is not None:
-        return hit
+    if hit is not None and hit[2].numel() == max(nbricks, 1):
+        # the buffers may have been last written on another stream
+        torch.cuda.current_stream(dev).wait_event(hit[3])
+        return hit[:3]
+    ncell = nxs * ny * nz
     return (torch.zeros(ncell, dtype=torch.uint8, device=dev),
             torch.zeros((ncell, 2), dtype=torch.float64, device=dev),
             torch.zeros(max(nbricks, 1), dtype=torch.uint8, device=dev))
 
 
 def _give_state(d):
-    """Return a model's state buffers to the pool (at most one set per slab size)."""
+    """Return a model's state buffers to the pool (at most one set per device)."""
     try:
+        torch = _torch()
         dev = d["device"]
-        key = (dev.index, d["nverts"].numel(), d["bricks"].numel())
+        idx = _dev_index(torch, dev)
         if d["bricks"].numel() >= 1:
-            _STATE_POOL.clear()
-            _STATE_POOL[key] = (d["nverts"], d["cells"], d["bricks"])
+            for k in [k for k in _STATE_POOL if k[0] == idx]:
+                del _STATE_POOL[k]
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            _STATE_POOL[(idx,) + tuple(d["layout"])] = (d["nverts"], d["cells"], d["bricks"], ev)
     except Exception:  # noqa: BLE001 -- recycling is an optimisation only
         pass
 
@@ -555,90 +570,149 @@ class JetModel:
                 arr[i].t0, arr[i].amp, arr[i].inv2s2 = t0, amp, inv2s2
         return e
 
-    def _ensure_filled(self):
+    def _ensure_filled(self, sync=True):
         """Run the grid fill (K1+K2) once; resolve near-tie vertices on the host with
-        the reference's own numpy expression so that the counts are bit-exact."""
-        if self._dev is not None:
-            return self._dev
+        the reference's own numpy expression so that the counts are bit-exact.
+
+        The fill reports its near-tie vertices through an asynchronous copy into pinned host
+        memory.  `sync=False` (the line-of-sight passes) returns without waiting for it: the
+        pass is queued right behind the fill and `_validate_fill` is consulted afterwards --
+        only if a host decision changes a vertex count (none does on the BASELINE grids) is the
+        pass repeated.  Every other consumer validates first."""
+        if self._dev is None:
+            self._launch_fill()
+        if sync:
+            self._validate_fill()
+        return self._dev
+
+    def _launch_fill(self, tie_cap=_TIE_CAPACITY):
         if 'travel' in self._overrides or 'vel' in self._overrides:
             raise NotImplementedError("user-assigned `ts` / `vel` grids are not supported by the "
                                       "CUDA path (`ion_fraction` and `temperature` are)")
         torch = _torch()
         lib = _cabi.load()
         dev = self._device()
-        ncell = (self._x_hi - self._x_lo) * self._ny * self._nz
-        t0 = _time.time()
+        nxs = self._x_hi - self._x_lo
+        self._fill_t0 = _time.time()
         if self.log:
             self._log.add_entry(mtype="INFO",
                                 entry="Calculating cells' fill factors/projected areas")
         with torch.cuda.device(dev):
             m = self._model_struct()
             nbricks = int(lib.rjp_brick_count(m))
-            nverts, cells, bricks = _take_state(torch, dev, ncell, nbricks)
-            ties = torch.empty((_TIE_CAPACITY, 4), dtype=torch.int32, device=dev)
+            nverts, cells, bricks = _take_state(torch, dev, nxs, self._ny, self._nz, nbricks)
+            # [0:8] counters ([0] = number of near-tie vertices), [8:] the tie list
+            tb = torch.empty(8 + 4 * tie_cap, dtype=torch.int32, device=dev)
+            tb[:8].zero_()
             work = torch.empty(nbricks + 4, dtype=torch.int32, device=dev)   # fill work list
-            counters = torch.zeros(8, dtype=torch.int32, device=dev)  # [0] n_ties
-            nray = (self._x_hi - self._x_lo) * self._nz
+            nray = nxs * self._nz
             extents = torch.empty((nray, 2), dtype=torch.int32, device=dev)
-            tie_cap = _TIE_CAPACITY
-            for attempt in range(3):
-                counters.zero_()
-                st = lib.rjp_fill_grid(m, nverts.data_ptr(), cells.data_ptr(),
-                                       bricks.data_ptr(), work.data_ptr(), ties.data_ptr(),
-                                       tie_cap,
-                                       counters.data_ptr(), extents.data_ptr(), self._stream())
-                _cabi.check(st, "rjp_fill_grid")
-                _launched(3)   # init_extents, fill_classify, fill_bricks kernels
-                c = counters.cpu().numpy()
-                if c[0] <= tie_cap:
-                    break
-                tie_cap = int(c[0]) + 1024
-                ties = torch.empty((tie_cap, 4), dtype=torch.int32, device=dev)
-            else:
-                raise _cabi.EngineError("grid fill: tie list did not converge")
-            n_ties = int(c[0])
+            st = lib.rjp_fill_grid(m, nverts.data_ptr(), cells.data_ptr(),
+                                   bricks.data_ptr(), work.data_ptr(), tb.data_ptr() + 32,
+                                   tie_cap, tb.data_ptr(), extents.data_ptr(), self._stream())
+            _cabi.check(st, "rjp_fill_grid")
+            _launched(3)   # init_extents, fill_classify, fill_bricks kernels
+            n_async = min(tie_cap, _TIE_ASYNC)
+            pin = torch.empty(8 + 4 * n_async, dtype=torch.int32, pin_memory=True)
+            pin.copy_(tb[:8 + 4 * n_async], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
             self._dev = {"nverts": nverts, "cells": cells, "bricks": bricks,
-                         "extents": extents, "model": m,
+                         "extents": extents, "model": m, "layout": (nxs, self._ny, self._nz),
                          "device": dev, "stream2": torch.cuda.Stream(device=dev),
-                         "n_ties": n_ties, "n_patched": 0}
-            if n_ties > 0:
-                self._resolve_ties(ties[:n_ties].cpu().numpy().astype(np.int64))
-            for name, field in (('xi', 8), ('temp', 9)):     # RJP_FIELD_XI, RJP_FIELD_TEMP
-                if name in self._overrides:
-                    arr = np.ascontiguousarray(
-                        np.asarray(self._overrides[name], dtype=np.float64)
-                        [self._x_lo:self._x_hi])
-                    if arr.shape != (self._x_hi - self._x_lo, self._ny, self._nz):
-                        raise ValueError(f"assigned grid has shape {arr.shape}")
-                    vals = torch.from_numpy(arr).to(dev)
-                    st = lib.rjp_override_cells(m, nverts.data_ptr(), field, vals.data_ptr(),
-                                                cells.data_ptr(), self._stream())
-                    _cabi.check(st, "rjp_override_cells")
-                    _launched()
+                         "cursor": torch.zeros(4, dtype=torch.int32, device=dev),
+                         "n_ties": None, "n_patched": 0,
+                         "tie_pending": (pin, ev, tb, tie_cap)}
+            self._apply_overrides()
             self._build_ray_list()
-        if self.log:
-            self.log.add_entry(mtype="INFO",
-                               entry=_time.strftime('Finished in %Hh%Mm%Ss',
-                                                    _time.gmtime(_time.time() - t0)))
         return self._dev
 
-    def _build_ray_list(self):
-        """Rays that cross the jet: the channel loop runs one CTA per listed ray."""
+    def _apply_overrides(self):
         torch = _torch()
         lib = _cabi.load()
         d = self._dev
+        dev = d["device"]
+        for name, field in (('xi', 8), ('temp', 9)):     # RJP_FIELD_XI, RJP_FIELD_TEMP
+            if name in self._overrides:
+                arr = np.ascontiguousarray(
+                    np.asarray(self._overrides[name], dtype=np.float64)
+                    [self._x_lo:self._x_hi])
+                if arr.shape != (self._x_hi - self._x_lo, self._ny, self._nz):
+                    raise ValueError(f"assigned grid has shape {arr.shape}")
+                vals = torch.from_numpy(arr).to(dev)
+                st = lib.rjp_override_cells(d["model"], d["nverts"].data_ptr(), field,
+                                            vals.data_ptr(), d["cells"].data_ptr(),
+                                            self._stream())
+                _cabi.check(st, "rjp_override_cells")
+                _launched()
+
+    def _validate_fill(self):
+        """Wait for the fill's tie report (not for anything queued behind it), let the host
+        decide the reported vertices and patch the cells whose count changes.  Returns True if
+        the state changed (passes launched meanwhile are stale and have been dropped)."""
+        d = self._dev
+        pend = d.pop("tie_pending", None) if d is not None else None
+        if pend is None:
+            return False
+        pin, ev, tb, tie_cap = pend
+        ev.synchronize()
+        n_ties = int(pin[0])
+        if n_ties > tie_cap:
+            # the list overflowed: fill again with room for every tie (never seen on real
+            # grids: dyadic axis-aligned grids report tens of vertices)
+            self._dev = None
+            self._cont = self._line = None
+            _give_state(d)
+            self._launch_fill(tie_cap=n_ties + 1024)
+            self._validate_fill()
+            return True
+        d["n_ties"] = n_ties
+        changed = False
+        if n_ties > 0:
+            if n_ties <= (pin.numel() - 8) // 4:
+                ties = pin[8:8 + 4 * n_ties].view(n_ties, 4).numpy()
+            else:
+                ties = tb[8:8 + 4 * n_ties].view(n_ties, 4).cpu().numpy()
+            changed = self._resolve_ties(ties.astype(np.int64))
+        if changed:
+            torch = _torch()
+            with torch.cuda.device(d["device"]):
+                self._apply_overrides()
+                self._build_ray_list()
+            self._cont = self._line = None
+            self._fields.clear()
+        if self.log:
+            self.log.add_entry(mtype="INFO",
+                               entry=_time.strftime('Finished in %Hh%Mm%Ss',
+                                                    _time.gmtime(_time.time() - self._fill_t0)))
+        return changed
+
+    def _build_ray_list(self):
+        """Ordered list of the rays that cross the jet; its length stays on the device (the
+        ray kernels read it there)."""
+        torch = _torch()
+        lib = _cabi.load()
+        d = self._dev
+        dev = d["device"]
         nray = d["extents"].shape[0]
-        rays = torch.empty(nray, dtype=torch.int32, device=d["device"])
-        n_act = torch.zeros(1, dtype=torch.int32, device=d["device"])
+        rays = torch.empty(max(nray, 1), dtype=torch.int32, device=dev)
+        counts = torch.empty(max(int(lib.rjp_ray_list_chunks(nray)), 1), dtype=torch.int32,
+                             device=dev)
+        n_act = torch.zeros(1, dtype=torch.int32, device=dev)
         st = lib.rjp_ray_list(d["extents"].data_ptr(), nray, rays.data_ptr(),
-                              n_act.data_ptr(), self._stream())
+                              counts.data_ptr(), n_act.data_ptr(), self._stream())
         _cabi.check(st, "rjp_ray_list")
-        _launched()
-        d["n_active"] = int(n_act.item())
-        # sorted: neighbouring CTAs of the ray kernels write neighbouring cube columns, and the
-        # sparse cube exchange between slabs packs / scatters coalesced
-        d["rays"] = torch.sort(rays[:max(d["n_active"], 1)])[0].contiguous()
+        _launched(2)
+        d["rays"], d["n_active_dev"], d["n_active_host"] = rays, n_act, None
         d["ray_meta"] = None
+
+    def _n_active(self):
+        """Number of jet-crossing rays of the slab on the HOST (blocks; only the sharded
+        exchange and diagnostics need it)."""
+        d = self._ensure_filled()
+        if d["n_active_host"] is None:
+            d["n_active_host"] = int(d["n_active_dev"].item())
+        return d["n_active_host"]
 
     def _decide_ties(self, I, J, K, dec):
         """{flat slab cell index: change of its vertex count} from the reference's own numpy
@@ -695,7 +769,7 @@ class JetModel:
             _TIE_DECISIONS[key] = delta
         d["n_patched"] = len(delta)
         if not delta:
-            return
+            return False
         dev = d["device"]
         idx = torch.tensor(sorted(delta), dtype=torch.int64, device=dev)
         old = d["nverts"][idx].to(torch.int64)
@@ -710,6 +784,7 @@ class JetModel:
                                  self._stream())
         _cabi.check(st, "rjp_patch_cells")
         _launched()
+        return True
 
     def _adopt_fill_factor(self, ffs):
         """Resume path (classes.py:78-84): take fill factors from a saved model instead
@@ -903,7 +978,7 @@ class JetModel:
         of the current epoch and the last line cube."""
         torch = _torch()
         lib = _cabi.load()
-        d = self._ensure_filled()
+        d = self._ensure_filled(sync=False)
         dev = d["device"]
         nxs, nz = self._x_hi - self._x_lo, self._nz
         key_c = (float(self._time), len(self._ejections))
@@ -928,7 +1003,8 @@ class JetModel:
             if line is None:
                 st = lib.rjp_integrate(d["model"], ep, ct, d["cells"].data_ptr(),
                                        d["extents"].data_ptr(), d["rays"].data_ptr(),
-                                       d["n_active"], em.data_ptr(), kff.data_ptr(),
+                                       d["n_active_dev"].data_ptr(), d["cursor"].data_ptr(),
+                                       em.data_ptr(), kff.data_ptr(),
                                        tsum.data_ptr(), cnt.data_ptr(), None, None, 0, 1,
                                        None, None, 0, 0, self._stream(), None)
             else:
@@ -945,7 +1021,8 @@ class JetModel:
                 side = self._fill_remote_constants(tau, flux) if self._world > 1 else None
                 st = lib.rjp_integrate(d["model"], ep, ct, d["cells"].data_ptr(),
                                        d["extents"].data_ptr(), d["rays"].data_ptr(),
-                                       d["n_active"], em.data_ptr(), kff.data_ptr(),
+                                       d["n_active_dev"].data_ptr(), d["cursor"].data_ptr(),
+                                       em.data_ptr(), kff.data_ptr(),
                                        tsum.data_ptr(), cnt.data_ptr(), ln,
                                        chans, nch, 1 if contsub else 0,
                                        tau.data_ptr() if want_tau else None,
@@ -959,10 +1036,13 @@ class JetModel:
             _cabi.check(st, "rjp_integrate")
             _launched(2 if line is None else 1 + (len(freqs) + 2047) // 2048)
         self._cont = {"key": key_c, "em": em, "kff": kff, "tsum": tsum, "cnt": cnt}
-        if line is None:
-            return self._cont
-        self._line = {"key": key_l, "tau": tau, "flux": flux}
-        return self._line
+        if line is not None:
+            self._line = {"key": key_l, "tau": tau, "flux": flux}
+        if self._validate_fill():
+            # a host-resolved near-tie changed a vertex count after this pass was queued:
+            # the state has been patched, integrate again
+            return self._pass(line, freqs, contsub, want_tau, want_flux)
+        return self._cont if line is None else self._line
 
     def _line_structs(self, line, freqs, dev):
         """Host scalars of the LTE line opacity (classes.py:1159-1169; rrls.py) and the
@@ -1087,7 +1167,7 @@ class JetModel:
             out = torch.empty((7, npix), dtype=torch.float64, device=dev)
             st = lib.rjp_los_means(d["model"], self._epoch_struct(), d["nverts"].data_ptr(),
                                    d["extents"].data_ptr(), d["rays"].data_ptr(),
-                                   d["n_active"], out.data_ptr(), self._stream())
+                                   d["n_active_dev"].data_ptr(), out.data_ptr(), self._stream())
             _cabi.check(st, "rjp_los_means")
             _launched()
         maps = self._host_image(out, lead=7)
@@ -1128,7 +1208,7 @@ class JetModel:
         from . import sharding
         d = self._dev
         if d.get("ray_meta") is None:
-            d["ray_meta"] = sharding.build_ray_meta(d["extents"], d["rays"][:d["n_active"]],
+            d["ray_meta"] = sharding.build_ray_meta(d["extents"], d["rays"][:self._n_active()],
                                                     self._x_lo, self._nx, self._nz, self._rank,
                                                     self._world, bounds=self._bounds)
         return d["ray_meta"]
@@ -1151,7 +1231,7 @@ class JetModel:
         # beside a long channel loop a light store grid interferes least; when this slab's loop
         # is shorter than the constant fill itself, the fill should run at full bandwidth
         ncube = (tau is not None) + (flux is not None)
-        t_loop = d["n_active"] * nch * 1.7e-7                       # ms, measured rate
+        t_loop = self._n_active() * nch * 1.7e-7                    # ms, measured rate
         t_fill = (nx - (self._x_hi - self._x_lo)) * nz * nch * ncube * 8 / 3.4e9   # ms, light grid
         light = 1 if t_loop > t_fill else 0
         # ONE launch for all other slabs (own rays skipped), queued before the channel loop so

@@ -101,3 +101,31 @@ def line_channels(nu0, nchan, chanw):
     """Channel centres nu0 + (k - (nchan-1)/2) * chanw, i.e. ContinuumRun.chan_freqs
     (classes.py:1897-1900) for bandwidth = nchan * chanw centred on nu0."""
     return nu0 - nchan * chanw / 2. + chanw / 2. + np.arange(nchan) * chanw
+
+
+# ------------------------------------------------------------------ large line-cube fixtures
+# (tools/make_golden_big.py runs the unmodified reference; tests/test_gpu_big_parity.py)
+_BENCH_PICK = (0, 40, 100, 160, 200, 230, 245, 252, 255, 256, 260, 275, 300, 350, 420, 511)
+
+
+def case_c2rrl():
+    """256^3, c_size 0.5 au: BASELINE configs[1] geometry with the H58a cube of configs[4]."""
+    return with_grid(base_params(), 256, 256, 256)
+
+
+def case_r256():
+    """The jet out to |r| = 256 au (what the 1024^3 / 0.5 au grid of configs[4] reaches) on a
+    128 x 128 x 512 grid with c_size 1.0 au."""
+    return with_grid(base_params(), 128, 128, 512, cs=1.0)
+
+
+# name -> (params factory, epoch [yr], line, {set: () -> channel offsets from nu0 [Hz]},
+#          sets that also store the contsub=True flux and intensity_rrl, ray stride)
+BIG_CASES = {
+    "c2rrl": (case_c2rrl, 1.0, "H58a",
+              {"pick": lambda: (np.array(_BENCH_PICK) - 255.5) * 1e5,
+               "uni": lambda: (np.arange(16) - 7.5) * 3.2e6}, (), 1),
+    "r256": (case_r256, 1.0, "H58a",
+             {"pick": lambda: (np.array(_BENCH_PICK) - 255.5) * 1e5,
+              "uni": lambda: (np.arange(8) - 3.5) * 4e5}, ("uni",), 3),
+}

@@ -51,3 +51,17 @@ def cancellation_floor_line(oj, chans):
         bnu = 2. * con.h * 1e7 * f ** 3. / (con.c * 1e2) ** 2. / \
             np.expm1(con.h * f / (con.k * tm[None])) * 1e-3 * om
     return 8 * np.finfo(np.float64).eps * np.abs(bnu)
+
+
+def flux_floors_uniform_t(params, freqs, t_mean):
+    """The two cancellation floors above for a jet of uniform temperature (q_T = q^d_T = 0:
+    the mean temperature of every jet-crossing ray is T_0 exactly), without an oracle run:
+    (continuum floor, line floor), each (nf,) in Jy/pixel."""
+    f = np.atleast_1d(np.asarray(freqs, dtype=np.float64))
+    om = np.arctan((params["grid"]["c_size"] * con.au) /
+                   (params["target"]["dist"] * con.parsec)) ** 2. / 1e-26
+    eps8 = 8 * np.finfo(np.float64).eps
+    ff = eps8 * 2. * f ** 2. * con.k / con.c ** 2. * t_mean * om
+    bnu = 2. * con.h * 1e7 * f ** 3. / (con.c * 1e2) ** 2. / \
+        np.expm1(con.h * f / (con.k * t_mean)) * 1e-3 * om
+    return ff, eps8 * np.abs(bnu)

@@ -78,7 +78,7 @@ def test_grid_that_misses_the_jet():
     p["geometry"]["r_0"] = 500.
     jm, oj = _pair(p)
     assert int(jm.n_verts_inside().sum()) == 0 == int(oj.n_verts_inside().sum())
-    assert jm._ensure_filled()["n_active"] == 0
+    assert jm._n_active() == 0
     chans = cases.line_channels(3.285e10, 9, 1e6)
     assert np.array_equal(jm.emission_measure(), np.zeros((16, 24)))
     assert np.array_equal(jm.optical_depth_ff(np.array([5e9, 1e10])), np.zeros((2, 16, 24)))

@@ -27,7 +27,8 @@ def test_sparse_walk_equals_dense_sweep(name):
     em, kff, tsum = (torch.empty(npix, dtype=torch.float64, device="cuda") for _ in range(3))
     cnt = torch.empty(npix, dtype=torch.int32, device="cuda")
     st = lib.rjp_integrate(d["model"], jm._epoch_struct(), jm._continuum_struct(),
-                           d["cells"].data_ptr(), None, None, 0, em.data_ptr(), kff.data_ptr(),
+                           d["cells"].data_ptr(), None, None, None, None, em.data_ptr(),
+                           kff.data_ptr(),
                            tsum.data_ptr(), cnt.data_ptr(), None, None, 0, 1, None, None,
                            0, 0, jm._stream(), None)
     _cabi.check(st, "rjp_integrate(dense)")
@@ -97,3 +98,46 @@ def test_recycled_state_equals_dense_fill():
     assert not np.any(per_brick & (bricks == 0))
     second.release()
     jetmodel.clear_state_pool()
+
+
+def test_state_pool_is_keyed_on_the_layout():
+    """Two models with the same number of cells and bricks but different (ny, nz): the flat
+    cell index and the brick ids depend on the layout, so the second model must not reuse the
+    first one's occupancy map."""
+    import copy
+    import rajepy_b200 as rb
+    from rajepy_b200 import jetmodel
+    log = rb.logger.Log(os.path.join(tempfile.mkdtemp(), "m.log"), verbose=False)
+    jetmodel.clear_state_pool()
+    pa = cases.with_grid(cases.base_params(), 32, 64, 128)
+    pb = cases.with_grid(cases.base_params(), 32, 128, 64)
+    first = rb.JetModel(pa, log=log)
+    first._ensure_filled()
+    first.release()
+    second = rb.JetModel(copy.deepcopy(pb), log=log)
+    got = second.n_verts_inside()
+    second.release()
+    jetmodel.clear_state_pool()
+    fresh = rb.JetModel(copy.deepcopy(pb), log=log)
+    want = fresh.n_verts_inside()
+    assert np.array_equal(got, want)
+    assert np.array_equal(np.nan_to_num(fresh.emission_measure()),
+                          np.nan_to_num(rb.JetModel(copy.deepcopy(pb), log=log).emission_measure()))
+    jetmodel.clear_state_pool()
+
+
+def test_ray_list_is_ordered_and_complete():
+    """rjp_ray_list: ascending slab-local ids of exactly the rays with a non-empty extent."""
+    import torch
+    import rajepy_b200 as rb
+    log = rb.logger.Log(os.path.join(tempfile.mkdtemp(), "m.log"), verbose=False)
+    for name in ("small", "inclined", "c1"):
+        jm = rb.JetModel(cases.CASES[name][0](), log=log)
+        d = jm._ensure_filled()
+        n = jm._n_active()
+        ext = d["extents"].cpu().numpy()
+        want = np.flatnonzero(ext[:, 0] < ext[:, 1])
+        got = d["rays"][:n].cpu().numpy()
+        assert n == want.size
+        assert np.array_equal(got, want)
+        jm.release()
