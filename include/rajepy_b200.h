@@ -205,17 +205,19 @@ int rjp_ray_list(const int32_t* extents, int64_t nray, int32_t* list, int32_t* c
 int64_t rjp_ray_list_chunks(int64_t nray);
 
 /* Line-of-sight pass (K3+K4+K5).  The ray kernels walk only the per-ray in-jet extents recorded
- * by the fill (persistent CTAs pull the rays of `ray_list`; *n_active is read on the device)
- * and run on `stream2` when one is given (NULL: same stream) beside the constant writer, which
- * streams the 0 / NaN of the rays that miss the jet with TMA bulk stores on `stream`.
+ * by the fill (the CTAs stride over `ray_list`; *n_active is read on the device) and run on
+ * `stream2` when one is given (NULL: same stream) beside the constant writer, which streams
+ * the 0 / NaN of the rays that miss the jet with TMA bulk stores on `stream`.
  * Replaces emission_measure (classes.py:1101-1128), optical_depth_ff (:1353-1447),
  * the nanmean temperature of intensity_ff (:1471-1473), optical_depth_rrl (:1130-1229)
  * and intensity_rrl/flux_rrl (:1231-1351).
  *   em, kff, tsum [nxs*nz] double, tcount [nxs*nz] int32 (always written)
  *   extents / ray_list / n_active (from rjp_fill_grid / rjp_ray_list); with any of them NULL
  *   (continuum-only passes) every cell of the state is swept instead (dense sweep).
- *   cursor: DEVICE scratch of 2 int32, zero-initialised by the caller ONCE; the line kernel
- *   uses it as its ticket counter and leaves it zero again (required for line passes).
+ *   n_active_hint: the caller's guess of *n_active on the HOST, or <= 0 if it has none.  It
+ *   only sizes the grid of the line kernel (one CTA per listed ray is fastest); any value
+ *   gives correct results, so a count remembered from an earlier model of the same
+ *   geometry is fine and nothing has to be read back from the device.
  *   line/ch may be NULL/nchan = 0 for a continuum-only pass; otherwise
  *   tau_rrl and/or flux_rrl ([nchan][nxs][nz] double) may each be NULL.
  *   contsub: 0 -> flux_rrl includes S_ff (what Pipeline requests, classes.py:2450).
@@ -227,7 +229,7 @@ int64_t rjp_ray_list_chunks(int64_t nray);
 int rjp_integrate(const rjp_model* m_host, const rjp_epoch* ep_host,
                   const rjp_continuum* cont_host, const rjp_cell* cells,
                   const int32_t* extents, const int32_t* ray_list, const int32_t* n_active,
-                  int32_t* cursor, double* em, double* kff, double* tsum,
+                  int32_t n_active_hint, double* em, double* kff, double* tsum,
                   int32_t* tcount, const rjp_line* line_host, const rjp_channels* ch_host,
                   int32_t nchan, int32_t contsub, double* tau_rrl, double* flux_rrl,
                   int64_t cube_plane, int64_t cube_offset, void* stream, void* stream2);
@@ -256,6 +258,19 @@ int rjp_scatter_rays(const double* in, int32_t n_stride, const int32_t* ray_ids,
 int rjp_fill_missed(const int32_t* extents, int64_t nray, int32_t nchan, int64_t cube_plane,
                     int64_t cube_offset, int64_t skip_lo, int64_t skip_hi, double* tau,
                     double* flux, int32_t light, void* stream);
+
+/* HOST-side assembly of a dense product cube (the hand-over to numpy, i.e. what
+ * optical_depth_rrl / flux_rrl return, classes.py:1215-1229, :1340-1351) from the packed columns
+ * of the jet-crossing rays -- so that only those columns have to cross PCIe:
+ *   dst_host[c * plane + r] = fill                          for every ray r not listed
+ *   dst_host[c * plane + ray_ids_host[k]] = cols_host[c * n_stride + k]
+ * for c < nchan.  ray_ids_host must be strictly ascending (what rjp_ray_list produces);
+ * cols_host is what rjp_pack_rays wrote, copied to the host.  The constants are written with
+ * streaming stores by `nthreads` host threads (<= 0: all hardware threads).  All pointers are
+ * HOST pointers; no CUDA call is made. */
+int rjp_host_assemble(double* dst_host, int64_t nchan, int64_t plane,
+                      const int32_t* ray_ids_host, int64_t n, const double* cols_host,
+                      int64_t n_stride, double fill, int32_t nthreads);
 
 /* Continuum epilogue (K5) for nfreq frequencies from one pass' kff/tsum/tcount:
  *   tau[f] = cff[f] * kff;  I[f] = iff[f] * Tmean * (1 - exp(-tau));  S[f] = I * omega_jy

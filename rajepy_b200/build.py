@@ -14,9 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.environ.get("RAJEPY_B200_LIB") or os.path.join(LIBDIR, "librajepy_b200.so")
-SOURCES = ["rjp_api.cu", "rjp_fill.cu", "rjp_integrate.cu"]
+SOURCES = ["rjp_api.cu", "rjp_fill.cu", "rjp_integrate.cu", "rjp_host.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
-              "-std=c++17", "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-std=c++17", "--shared", "-Xcompiler", "-fPIC,-pthread", "-Xptxas", "-v"]
 
 
 def _nvcc():

@@ -15,7 +15,7 @@ int rjp_launch_field(const rjp_model*, const rjp_epoch*, const uint8_t*, int32_t
                      cudaStream_t);
 int rjp_launch_integrate(const rjp_model*, const rjp_epoch*, const rjp_continuum*,
                          const rjp_cell*, const int32_t*, const int32_t*, const int32_t*,
-                         int32_t*, double*, double*, double*, int32_t*, const rjp_line*,
+                         int, double*, double*, double*, int32_t*, const rjp_line*,
                          const rjp_channels*, int, int, double, double*, double*, long long,
                          long long, cudaStream_t, cudaStream_t);
 int rjp_launch_fill_missed(const int32_t*, long long, int, long long, long long, long long,
@@ -135,7 +135,7 @@ extern "C" int rjp_ray_list(const int32_t* extents, int64_t nray, int32_t* list,
 extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_continuum* ct,
                              const rjp_cell* cells, const int32_t* extents,
                              const int32_t* ray_list, const int32_t* n_active,
-                             int32_t* cursor, double* em,
+                             int32_t n_active_hint, double* em,
                              double* kff, double* tsum, int32_t* tcount, const rjp_line* ln,
                              const rjp_channels* ch, int32_t nchan, int32_t contsub,
                              double* tau_rrl, double* flux_rrl, int64_t cube_plane,
@@ -149,10 +149,11 @@ extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_
     if (!ln || !ch || !ch->dnu || !ch->nu || !ch->cff || !ch->aff || !ch->bnu)
       return RJP_ERR_ARG;
     if (!tau_rrl && !flux_rrl) return RJP_ERR_ARG;
-    if (!extents || !ray_list || !n_active || !cursor) return RJP_ERR_ARG;
+    if (!extents || !ray_list || !n_active) return RJP_ERR_ARG;
     if (cube_plane < 0 || cube_offset < 0) return RJP_ERR_ARG;
   }
-  return check_launch(rjp_launch_integrate(m, ep, ct, cells, extents, ray_list, n_active, cursor,
+  return check_launch(rjp_launch_integrate(m, ep, ct, cells, extents, ray_list, n_active,
+                                           n_active_hint,
                                            em, kff, tsum, tcount,
                                            ln, ch, nchan, contsub, ln ? ln->dn_max : 0.0,
                                            tau_rrl, flux_rrl, cube_plane, cube_offset,

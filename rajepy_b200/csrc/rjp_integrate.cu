@@ -333,102 +333,147 @@ __device__ __forceinline__ double planck_factor(const LineEntry& e, double dn) {
 //   Ray i of `extents` is element offset + i of every cube plane (plane = elements per
 // plane): a slab writes into its rows of a full-size cube this way.  Rays in
 // [skip_lo, skip_hi) are left alone (multi-GPU: the own slab inside the global ray range).
-constexpr int CT_TILE = 1024;    // rays per tile (8 KB of doubles)
+constexpr int CT_TILE = 1024;    // rays per tile
+constexpr int CT_SRC = 1024;     // doubles per shared-memory source tile (8 KB per bulk store)
 #ifndef RJP_CT_CG
 #define RJP_CT_CG 32             // channel planes per work item
 #endif
 
 __device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+#ifndef RJP_NO_EVICT_FIRST
+  // the constants are never read again on the device: first in line for eviction, so that
+  // they do not push the ray kernels' partially written sectors out of L2
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               :: "l"(gdst), "r"(ssrc), "r"(bytes), "l"(pol) : "memory");
+#else
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                :: "l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+#endif
 }
 
-__global__ void __launch_bounds__(32)
-const_tiles_kernel(const int2* __restrict__ extents, size_t nray, int nchan,
-                   double* __restrict__ em, double* __restrict__ kff,
-                   double* __restrict__ tsum, int32_t* __restrict__ tcount,
-                   double* __restrict__ tau, double* __restrict__ flux, size_t plane,
-                   size_t offset, size_t skip_lo, size_t skip_hi, int use_bulk) {
-  __shared__ __align__(128) double s_zero[CT_TILE];
-  __shared__ __align__(128) double s_nan[CT_TILE];
-  RJP_STAMP_BEGIN(1)
-  const int lane = threadIdx.x;
-  const double nanv = dnan();
-  for (int i = lane; i < CT_TILE; i += 32) {
+// Column stores of the ray kernels: 8 bytes per (ray, channel), neighbouring rays (other
+// CTAs) complete the 32-byte sector a little later
+__device__ __forceinline__ void st_column(double* p, double v) { *p = v; }
+
+struct ConstJob {      // what the constant writer needs (kernel-argument block)
+  const int2* extents;
+  size_t nray;
+  int nchan;
+  double *em, *kff, *tsum;
+  int32_t* tcount;
+  double *tau, *flux;
+  size_t plane, offset, skip_lo, skip_hi;
+  int use_bulk;
+};
+
+__device__ __forceinline__ size_t const_items(const ConstJob& j) {
+  const size_t ntiles = (j.nray + CT_TILE - 1) / CT_TILE;
+  return ntiles * (size_t)(j.nchan > 0 ? (j.nchan + RJP_CT_CG - 1) / RJP_CT_CG : 1);
+}
+
+// Fill the two source tiles (all threads of the CTA) and publish them to the async proxy.
+__device__ __forceinline__ void const_sources(double* s_zero, double* s_nan) {
+  for (int i = threadIdx.x; i < CT_SRC; i += blockDim.x) {
     s_zero[i] = 0.0;
-    s_nan[i] = nanv;
+    s_nan[i] = dnan();
   }
-  __syncwarp();
-  // make the generic-proxy writes above visible to the async proxy (TMA reads)
+  __syncthreads();
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  const uint32_t a_zero = (uint32_t)__cvta_generic_to_shared(s_zero);
-  const uint32_t a_nan = (uint32_t)__cvta_generic_to_shared(s_nan);
-  const size_t ntiles = (nray + CT_TILE - 1) / CT_TILE;
-  const int ncg = nchan > 0 ? (nchan + RJP_CT_CG - 1) / RJP_CT_CG : 1;
-  const size_t nitems = ntiles * (size_t)ncg;
-  // item = tile * ncg + channel group; consecutive items go to different CTAs
-  for (size_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const size_t t = item / ncg;
-    const int cg = (int)(item - t * ncg);
-    const size_t r0 = t * CT_TILE;
-    // bit i of `miss`: ray r0 + 32 i + lane misses the jet (and is not in the skip range);
-    // bit i of `valid`: that ray exists
-    unsigned miss = 0u, valid = 0u;
-#pragma unroll 8
-    for (int i = 0; i < CT_TILE / 32; ++i) {
-      const size_t ray = r0 + 32 * i + lane;
-      if (ray < nray) {
-        valid |= 1u << i;
-        if (!(ray >= skip_lo && ray < skip_hi)) {
-          const int2 e = __ldg(extents + ray);
-          if (e.x >= e.y) miss |= 1u << i;
-        }
+}
+
+// One work item = (tile of CT_TILE rays) x (group of RJP_CT_CG channel planes), done by the
+// ONE warp of the calling CTA.
+__device__ __forceinline__ void const_item(const ConstJob& j, size_t item, const double* s_zero,
+                                           const double* s_nan) {
+  const int NT = 32, g = threadIdx.x & 31;
+  const int ncg = j.nchan > 0 ? (j.nchan + RJP_CT_CG - 1) / RJP_CT_CG : 1;
+  const size_t t = item / ncg;
+  const int cg = (int)(item - t * ncg);
+  const size_t r0 = t * CT_TILE;
+  const int per = CT_TILE / NT;                       // rays per thread (<= 32)
+  // bit i of `miss`: ray r0 + NT i + g misses the jet (and is not in the skip range);
+  // bit i of `valid`: that ray exists
+  unsigned miss = 0u, valid = 0u;
+  for (int i = 0; i < per; ++i) {
+    const size_t ray = r0 + (size_t)NT * i + g;
+    if (ray < j.nray) {
+      valid |= 1u << i;
+      if (!(ray >= j.skip_lo && ray < j.skip_hi)) {
+        const int2 e = __ldg(j.extents + ray);
+        if (e.x >= e.y) miss |= 1u << i;
       }
     }
-    if (cg == 0 && em != nullptr) {     // the four sky images, once per tile
-#pragma unroll 4
-      for (int i = 0; i < CT_TILE / 32; ++i) {
-        if (miss >> i & 1u) {
-          const size_t ray = r0 + 32 * i + lane;
-          em[ray] = 0.0;
-          kff[ray] = 0.0;
-          tsum[ray] = 0.0;
-          tcount[ray] = 0;
-        }
+  }
+  if (cg == 0 && j.em != nullptr) {     // the four sky images, once per tile
+    for (int i = 0; i < per; ++i) {
+      if (miss >> i & 1u) {
+        const size_t ray = r0 + (size_t)NT * i + g;
+        j.em[ray] = 0.0;
+        j.kff[ray] = 0.0;
+        j.tsum[ray] = 0.0;
+        j.tcount[ray] = 0;
       }
     }
-    if (nchan <= 0) continue;
-    const int c_lo = cg * RJP_CT_CG;
-    const int c_hi = (c_lo + RJP_CT_CG < nchan) ? c_lo + RJP_CT_CG : nchan;
-    const size_t n_in = (nray - r0 < (size_t)CT_TILE) ? nray - r0 : (size_t)CT_TILE;
-    // whole tile constant?  (a short last tile counts if all of its rays miss and its
-    // byte count is a multiple of 16)
-    const bool all_const = __all_sync(0xffffffffu, miss == valid) && (n_in & 1) == 0;
-    if (all_const && use_bulk) {
-      if (lane == 0) {
-        const uint32_t bytes = (uint32_t)(n_in * sizeof(double));
-        for (int c = c_lo; c < c_hi; ++c) {
-          const size_t o = (size_t)c * plane + offset + r0;
-          if (tau) bulk_store(tau + o, a_zero, bytes);
-          if (flux) bulk_store(flux + o, a_nan, bytes);
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-    } else if (__any_sync(0xffffffffu, miss != 0u)) {
+  }
+  if (j.nchan <= 0) return;
+  const int c_lo = cg * RJP_CT_CG;
+  const int c_hi = (c_lo + RJP_CT_CG < j.nchan) ? c_lo + RJP_CT_CG : j.nchan;
+  const size_t n_in = (j.nray - r0 < (size_t)CT_TILE) ? j.nray - r0 : (size_t)CT_TILE;
+  // whole tile constant?  (a short last tile counts if all of its rays miss and its byte
+  // count is a multiple of 16)
+  const int same = __all_sync(0xffffffffu, miss == valid);
+  const int any = __any_sync(0xffffffffu, miss != 0u);
+  if (same && (n_in & 1) == 0 && j.use_bulk) {
+    if (g == 0) {
+      const uint32_t a_zero = (uint32_t)__cvta_generic_to_shared(s_zero);
+      const uint32_t a_nan = (uint32_t)__cvta_generic_to_shared(s_nan);
       for (int c = c_lo; c < c_hi; ++c) {
-        const size_t o = (size_t)c * plane + offset + r0 + lane;
-#pragma unroll 8
-        for (int i = 0; i < CT_TILE / 32; ++i) {
-          if (miss >> i & 1u) {
-            if (tau) tau[o + 32 * i] = 0.0;
-            if (flux) flux[o + 32 * i] = nanv;
-          }
+        const size_t o = (size_t)c * j.plane + j.offset + r0;
+        for (size_t k = 0; k < n_in; k += CT_SRC) {
+          const uint32_t bytes =
+              (uint32_t)((n_in - k < (size_t)CT_SRC ? n_in - k : (size_t)CT_SRC) * sizeof(double));
+          if (j.tau) bulk_store(j.tau + o + k, a_zero, bytes);
+          if (j.flux) bulk_store(j.flux + o + k, a_nan, bytes);
+        }
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  } else if (any) {
+    const double nanv = dnan();
+    for (int c = c_lo; c < c_hi; ++c) {
+      const size_t o = (size_t)c * j.plane + j.offset + r0 + g;
+      for (int i = 0; i < per; ++i) {
+        if (miss >> i & 1u) {
+          if (j.tau) j.tau[o + (size_t)NT * i] = 0.0;
+          if (j.flux) j.flux[o + (size_t)NT * i] = nanv;
         }
       }
     }
   }
-  // the shared-memory source must outlive the reads, the writes must have landed at exit
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// the shared-memory sources must outlive the reads, the writes must have landed at exit
+__device__ __forceinline__ void const_drain() {
+  if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __syncthreads();
+}
+
+// The constant writer: every warp of the grid takes work items round-robin (consecutive items
+// go to different CTAs); the warps of a CTA share the two source tiles.
+__global__ void __launch_bounds__(256)
+const_tiles_kernel(const ConstJob job) {
+  __shared__ __align__(128) double s_zero[CT_SRC];
+  __shared__ __align__(128) double s_nan[CT_SRC];
+  RJP_STAMP_BEGIN(1)
+  const_sources(s_zero, s_nan);
+  const size_t nitems = const_items(job);
+  const int nwarp = blockDim.x >> 5, wrp = threadIdx.x >> 5;
+  for (size_t item = (size_t)wrp * gridDim.x + blockIdx.x; item < nitems;
+       item += (size_t)gridDim.x * nwarp)
+    const_item(job, item, s_zero, s_nan);
+  const_drain();
   RJP_STAMP_END(1)
 }
 
@@ -578,18 +623,20 @@ ray_compact_kernel(const int2* __restrict__ extents, int nray,
 // which spilled), which is what lets the kernel fit more warps per SM.
 // GCH = channels per thread (8 for whole cubes; 4 / 2 when a rank of a channel-sharded run
 // owns only 128 / 64 channels, so that a one-warp CTA still covers them without idle slots).
-// Persistent: the CTAs pull rays from the list with a ticket counter (`cursor`, two ints that
-// the last CTA to leave resets to zero) and read the list length on the device, so the host
-// never has to know how many rays cross the jet.
+// The list length is read on the device (the host never has to know how many rays cross the
+// jet); see the ray loop for how the rays are dealt to the CTAs.
 template <int MAXT, int MINB, bool UNI, int GCH>
+#ifdef RJP_LINE_MAXNREG
+__global__ void __maxnreg__(RJP_LINE_MAXNREG)
+#else
 __global__ void __launch_bounds__(MAXT, MINB)
+#endif
 integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
                       const rjp_line ln, const rjp_channels ch, const int nchan,
                       const int c_first, const int contsub, const double dn_max,
                       const double2* __restrict__ cells, const int2* __restrict__ extents,
                       const int32_t* __restrict__ ray_list,
-                      const int32_t* __restrict__ n_active_dev, int32_t* __restrict__ cursor,
-                      double* __restrict__ em,
+                      const int32_t* __restrict__ n_active_dev, double* __restrict__ em,
                       double* __restrict__ kff, double* __restrict__ tsum,
                       int32_t* __restrict__ tcount, double* __restrict__ tau_rrl,
                       double* __restrict__ flux_rrl, const size_t plane,
@@ -600,10 +647,9 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   // (both are 80 bytes; +3 zero-amplitude pads for the 4-cell batches of the fp64 path)
   __shared__ __align__(16) unsigned char s_raw[(MAXT + 4) * sizeof(LineEntry)];
   __shared__ float4 s_tab[VT_TAB_F4];
-  __shared__ double s_part[3][MAXT];
-  __shared__ int s_pcnt[MAXT];
+  __shared__ double s_part[3][MAXT / 32];
+  __shared__ int s_pcnt[MAXT / 32];
   __shared__ int s_woff[2][MAXT / 32 + 1];
-  __shared__ int s_ticket;
   static_assert(sizeof(LineEntry) == sizeof(FastEntry), "shared batch buffer");
   RJP_STAMP_BEGIN(0)
   stage_params(&s_p, m, ep);
@@ -625,7 +671,8 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   double dn[UNI ? 1 : GCH];
   f32x2 dnf2[UNI ? 1 : GCH / 2];
   const double dstep = ln.chan_step * (double)NT;        // UNI: dn_j = dn[0] + j dstep
-  const float dstepf = (float)dstep;
+  float dstepf = (float)dstep;
+  asm volatile("" : "+f"(dstepf));   // keep it in a register (rematerialising costs 3 slots)
   if constexpr (UNI) {
     dn[0] = ln.chan_dnu0 + (double)(c_first + g) * ln.chan_step;
     dnf2[0] = pk2((float)dn[0], (float)dn[0]);
@@ -637,15 +684,18 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
     for (int j = 0; j < GCH; j += 2) dnf2[j >> 1] = pk2((float)dn[j], (float)dn[j + 1]);
   }
 
-  for (;;) {                                         // one jet-crossing ray per iteration
-  if (g == 0) s_ticket = atomicAdd(cursor, 1);
   __syncthreads();
-  const int ticket = s_ticket;
-  if (ticket >= n_active) break;
+  // ray number blockIdx.x, + gridDim.x, ... of the ordered list.  The grid is a fixed multiple
+  // of what fits on the device (the host never knows how many rays cross the jet): CTAs
+  // beyond the list leave at once, a long list gives every CTA a few rays.  Measured on B200:
+  // a grid of exactly-resident CTAs pulling rays from a ticket counter is 7 % SLOWER (5.61 vs
+  // 5.25 ms at 1024^2 rays x 512 channels) -- CTAs of one age advance in lockstep, young CTAs
+  // beside old ones overlap their latency-bound cell preparation with the others' channel loop.
+  for (int ticket = blockIdx.x; ticket < n_active; ticket += gridDim.x) {
   const int ray = ray_list[ticket];                // slab-local ray index = xl * nz + iz
+  const int2 ext = extents[ray];
   const int xl = ray / m.nz, iz = ray - xl * m.nz;
   const int ix = m.x_lo + xl;
-  const int2 ext = extents[ray];
   double acc[GCH];
 #pragma unroll
   for (int j = 0; j < GCH; ++j) acc[j] = 0.0;
@@ -779,15 +829,25 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
     __syncthreads();
   }
 
-  // the ray's continuum sums (needed by the flux epilogue): reduce the NT partials
-  s_part[0][g] = ca.kff;
-  s_part[1][g] = ca.tsum;
-  s_part[2][g] = ca.em;
-  s_pcnt[g] = ca.cnt;
+  // the ray's continuum sums (needed by the flux epilogue): warp shuffles, then the warps'
+  // partials through shared memory
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ca.kff += __shfl_xor_sync(0xffffffffu, ca.kff, o);
+    ca.tsum += __shfl_xor_sync(0xffffffffu, ca.tsum, o);
+    ca.em += __shfl_xor_sync(0xffffffffu, ca.em, o);
+    ca.cnt += __shfl_xor_sync(0xffffffffu, ca.cnt, o);
+  }
+  if (lane == 0) {
+    s_part[0][wrp] = ca.kff;
+    s_part[1][wrp] = ca.tsum;
+    s_part[2][wrp] = ca.em;
+    s_pcnt[wrp] = ca.cnt;
+  }
   __syncthreads();
   double kray = 0.0, ts = 0.0, emr = 0.0;
   int cn = 0;
-  for (int i = 0; i < NT; ++i) {
+  for (int i = 0; i < nwarps; ++i) {
     kray += s_part[0][i];
     ts += s_part[1][i];
     emr += s_part[2][i];
@@ -807,7 +867,7 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   for (int j = 0; j < GCH; ++j) {
     const int c = g + j * NT;
     if (c >= nchan) break;
-    if (tau_rrl) tau_rrl[(size_t)c * plane + cube_offset + ray] = acc[j];
+    if (tau_rrl) st_column(tau_rrl + (size_t)c * plane + cube_offset + ray, acc[j]);
     if (flux_rrl) {
       double s = dnan();
       if (cn > 0) {
@@ -817,18 +877,11 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
         s = bnu * ec * (1.0 - exp(-acc[j]));
         if (!contsub) s += __ldg(ch.aff + c) * (tmean * (1.0 - ec));
       }
-      flux_rrl[(size_t)c * plane + cube_offset + ray] = s;
+      st_column(flux_rrl + (size_t)c * plane + cube_offset + ray, s);
     }
   }
+  __syncthreads();   // s_part / the batch buffer are reused by the next ray
   }  // ray loop
-  // the last CTA to leave re-arms the ticket counter for the next launch
-  if (g == 0) {
-    __threadfence();
-    if (atomicAdd(cursor + 1, 1) == (int)gridDim.x - 1) {
-      cursor[0] = 0;
-      cursor[1] = 0;
-    }
-  }
   RJP_STAMP_END(0)
 }
 
@@ -1041,7 +1094,7 @@ static bool bulk_ok(const double* tau, const double* flux, size_t plane, size_t 
 extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
                                     const rjp_continuum* ct, const rjp_cell* cells,
                                     const int32_t* extents, const int32_t* ray_list,
-                                    const int32_t* n_active, int32_t* cursor, double* em,
+                                    const int32_t* n_active, int n_hint, double* em,
                                     double* kff, double* tsum, int32_t* tcount,
                                     const rjp_line* ln, const rjp_channels* ch, int nchan,
                                     int contsub, double dn_max, double* tau_rrl,
@@ -1066,37 +1119,41 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
   const size_t plane = cube_plane > 0 ? (size_t)cube_plane : nray;
   const size_t coff = cube_plane > 0 ? (size_t)cube_offset : 0;
   if (plane < coff + nray) return RJP_ERR_ARG;
-  if (lines && cursor == nullptr) return RJP_ERR_ARG;
   set_carveouts();
   const int sms = device_info().sms;
+  const bool bulk = bulk_ok(tau_rrl, flux_rrl, plane, coff, nray);
   cudaEvent_t fork = nullptr, join = nullptr;
   cudaStream_t ls = stream;
   if (stream2 != nullptr && stream2 != stream) {
-    // fork (before the constant fill is queued): the issue-bound ray walk on stream2 runs
-    // beside the write-bound constant fill on stream
+    // fork (before the constant fill is queued): the ray walk on stream2 runs beside the
+    // write-bound constant fill on stream
     if (pass_events(&fork, &join) != RJP_OK) return RJP_ERR_CUDA;
     if (cudaEventRecord(fork, stream) != cudaSuccess ||
         cudaStreamWaitEvent(stream2, fork, 0) != cudaSuccess)
       return RJP_ERR_CUDA;
     ls = stream2;
   }
+  ConstJob job = {ex2, nray, lines ? nchan : 0, em, kff, tsum, tcount, tau_rrl, flux_rrl,
+                  plane, coff, 0, 0, bulk ? 1 : 0};
   // constants of the rays that miss the jet: one warp per SM streams whole constant tiles
   // with TMA bulk stores; launched first so that it is resident beside the ray kernels
-  {
-    const int per_sm = env_int("RJP_WRITER_PER_SM", lines ? 1 : 2);
+  if (!env_int("RJP_SKIP_WRITER", 0)) {   // (debug knob: time the ray kernels alone)
+    // beside a channel loop: few CTAs of several warps, so that only a few SMs give up a
+    // slot of the (register-bound) channel loop; alone: one CTA of 4 warps on every SM
+    const int ctas = env_int("RJP_WRITER_CTAS", lines ? sms / 4 : sms);
+    const int warps = env_int("RJP_WRITER_WARPS", 4);
     const size_t ntiles = (nray + CT_TILE - 1) / CT_TILE;
     const size_t items = ntiles * (size_t)(lines ? (nchan + RJP_CT_CG - 1) / RJP_CT_CG : 1);
-    size_t grid = (size_t)sms * per_sm;
-    if (grid > items) grid = items;
-    const_tiles_kernel<<<(unsigned)grid, 32, 0, stream>>>(
-        ex2, nray, lines ? nchan : 0, em, kff, tsum, tcount, tau_rrl, flux_rrl, plane, coff, 0, 0,
-        bulk_ok(tau_rrl, flux_rrl, plane, coff, nray) ? 1 : 0);
+    size_t grid = (size_t)(ctas > 0 ? ctas : 1);
+    if (grid * warps > items) grid = (items + warps - 1) / warps;
+    const_tiles_kernel<<<(unsigned)grid, 32 * warps, 0, stream>>>(job);
   }
-  if (lines) {
+  if (lines && !env_int("RJP_SKIP_LINES", 0)) {
     // channel blocks of at most 8 * 256 channels per launch; the first one also writes the
     // continuum images of its rays
-    for (int c0 = 0; c0 < nchan; c0 += GCH_MAX * LINE_THREADS) {
-      const int nc = (nchan - c0 < GCH_MAX * LINE_THREADS) ? nchan - c0 : GCH_MAX * LINE_THREADS;
+    const int cblock = env_int("RJP_CHAN_BLOCK", GCH_MAX * LINE_THREADS);   // (experiments)
+    for (int c0 = 0; c0 < nchan; c0 += cblock) {
+      const int nc = (nchan - c0 < cblock) ? nchan - c0 : cblock;
       rjp_channels cb = *ch;
       cb.dnu += c0; cb.nu += c0; cb.cff += c0; cb.aff += c0; cb.bnu += c0;
       const size_t off = (size_t)c0 * plane;
@@ -1120,11 +1177,12 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
       if (force_t > 0 && uni && force_t * GCH_MAX >= nc) { threads = force_t; gch = GCH_MAX; }
 #define RJP_LAUNCH_LINE(T, B, U, G)                                                           \
   do {                                                                                        \
-    size_t grid_ = (size_t)sms * (B);                                                         \
+    size_t grid_ = n_hint > 0 ? (size_t)n_hint                                                \
+                              : (size_t)sms * (B) * (size_t)env_int("RJP_GRID_FACTOR", 16);   \
     if (grid_ > nray) grid_ = nray;                                                           \
     integrate_line_kernel<T, B, U, G><<<(unsigned)grid_, threads, 0, ls>>>(                   \
-        *m, *ep, *ct, *ln, cb, nc, c0, contsub, dn_max, c4, ex2, ray_list, n_active, cursor,  \
-        em_o, kff, tsum, tcount, t_out, f_out, plane, coff);                                  \
+        *m, *ep, *ct, *ln, cb, nc, c0, contsub, dn_max, c4, ex2, ray_list, n_active, em_o,    \
+        kff, tsum, tcount, t_out, f_out, plane, coff);                                        \
   } while (0)
       if (threads <= 32 && uni) {
         if (gch == 2) RJP_LAUNCH_LINE(32, 16, true, 2);
@@ -1177,12 +1235,14 @@ extern "C" int rjp_launch_fill_missed(const int32_t* extents, long long nray, in
   // constants of the OTHER slabs' rays); otherwise enough warps to reach the HBM write peak
   const size_t ntiles = ((size_t)nray + CT_TILE - 1) / CT_TILE;
   const size_t items = ntiles * (size_t)((nchan + RJP_CT_CG - 1) / RJP_CT_CG);
-  size_t grid = (size_t)sms * (light ? 1 : env_int("RJP_WRITER_PER_SM_ALONE", 4));
-  if (grid > items) grid = items;
-  const_tiles_kernel<<<(unsigned)grid, 32, 0, stream>>>(
-      reinterpret_cast<const int2*>(extents), (size_t)nray, nchan, nullptr, nullptr, nullptr,
-      nullptr, tau, flux, (size_t)plane, (size_t)offset, (size_t)skip_lo, (size_t)skip_hi,
-      bulk_ok(tau, flux, (size_t)plane, (size_t)offset, (size_t)nray) ? 1 : 0);
+  const int warps = 4;
+  size_t grid = light ? (size_t)sms / 4 : (size_t)sms;
+  if (grid * warps > items) grid = (items + warps - 1) / warps;
+  ConstJob job = {reinterpret_cast<const int2*>(extents), (size_t)nray, nchan, nullptr, nullptr,
+                  nullptr, nullptr, tau, flux, (size_t)plane, (size_t)offset, (size_t)skip_lo,
+                  (size_t)skip_hi,
+                  bulk_ok(tau, flux, (size_t)plane, (size_t)offset, (size_t)nray) ? 1 : 0};
+  const_tiles_kernel<<<(unsigned)grid, 32 * warps, 0, stream>>>(job);
   return RJP_OK;
 }
 

@@ -118,11 +118,18 @@ def write_model_fits(model, data, filename, image_type, freq=None):
     cards = build_header(model, data, image_type, freq)
     hdr = ''.join(cards)
     hdr += ' ' * (-len(hdr) % BLOCK)
-    raw = np.ascontiguousarray(data).astype('>f8').tobytes()
-    raw += b'\0' * (-len(raw) % BLOCK)
+    flat = np.ascontiguousarray(data).reshape(-1)
     with open(filename, 'wb') as f:
         f.write(hdr.encode('ascii'))
-        f.write(raw)
+        step = 1 << 23                    # 64 MB of big-endian doubles at a time
+        for i in range(0, flat.size, step):
+            f.write(flat[i:i + step].astype('>f8').tobytes())
+        f.write(b'\0' * (-(flat.size * 8) % BLOCK))
+
+
+def read_fits_data(filename):
+    """Data array of a primary HDU (what `fits.open(f)[0].data` gives, classes.py:2431)."""
+    return read_fits(filename)[1]
 
 
 def read_fits(filename):

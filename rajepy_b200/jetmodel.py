@@ -53,10 +53,30 @@ _PLANE_WEIGHTS = {}     # slab-balancing estimate per geometry (host work, ~20 m
 _LINE_STRUCTS = {}      # line constants + per-channel device arrays
 _TIE_DECISIONS = {}     # host re-decisions of near-tie vertices per (geometry, slab, ties)
 _CONT_COEFFS = {}       # per-frequency continuum coefficients on the device
+_N_ACTIVE = {}          # jet-crossing rays per (geometry, grid, slab): grid size of the line kernel
 
 
 def _dev_index(torch, dev):
     return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
+# Hand-over of dense cubes to the host (JetModel._host_cube): measured rates of the two engines
+# that fill the host array side by side -- host threads assembling planes from the packed
+# jet-crossing columns, and the GPU's copy engine writing whole planes over PCIe.
+_HANDOVER = {"cpu_gbs": None, "dma_gbs": None}
+
+
+def _host_threads():
+    env = os.environ.get("RAJEPY_B200_HOST_THREADS")
+    if env:
+        return max(1, int(env))
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    # one process per GPU: the ranks of a node share the cores
+    n //= max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return max(1, min(n, 64))
 
 
 def _take_state(torch, dev, nxs, ny, nz, nbricks):
@@ -107,15 +127,21 @@ class JetModel:
     @classmethod
     def load_model(cls, model_file, **kwargs):
         """Load a model saved with `save` (classes.py:48-88)."""
+        from .compat import load_pickle
         model_file = os.path.expanduser(model_file)
-        with open(model_file, 'rb') as f:
-            loaded = pickle.load(f)
-        if 'log' in loaded and loaded['log'] is not None:
-            new_jm = cls(loaded["params"], log=loaded['log'], **kwargs)
-        else:
-            dcy_ = os.path.expanduser('~')
-            new_jm = cls(loaded["params"], log=logger.Log(dcy_ + os.sep + 'temp.log'),
-                         **kwargs)
+        loaded = load_pickle(model_file)     # also reads files written by the reference
+        log = kwargs.pop('log', None)
+        if log is None:
+            log = loaded.get('log')
+            if log is not None and not os.path.isdir(os.path.dirname(
+                    os.path.abspath(log.filename))):
+                # saved on another machine / in a directory that is gone: keep the entries,
+                # continue the log beside the save file
+                log._filename = os.path.join(os.path.dirname(os.path.abspath(model_file)),
+                                             os.path.basename(log.filename))
+        if log is None:
+            log = logger.Log(os.path.expanduser('~') + os.sep + 'temp.log')
+        new_jm = cls(loaded["params"], log=log, **kwargs)
         if loaded.get('ffs') is not None:
             new_jm._adopt_fill_factor(loaded['ffs'])
         new_jm.time = loaded['time']
@@ -145,7 +171,7 @@ class JetModel:
         return mod.params
 
     def __init__(self, params, log=None, device=None, shard=None, balance=True,
-                 host_ranks=None):
+                 host_ranks=None, shard_axis='x'):
         if isinstance(params, dict):
             self._params = params
         elif isinstance(params, str):
@@ -220,6 +246,17 @@ class JetModel:
         # device side
         self._device_arg = device
         if shard is None:
+            shard = (0, 1)
+        if shard_axis not in ('x', 'channel'):
+            raise ValueError("shard_axis must be 'x' or 'channel'")
+        # shard_axis='channel': every rank holds the whole grid and integrates a contiguous
+        # block of the channels of a line cube (sharding.chan_bounds); continuum products are
+        # replicated, cube planes stay with their rank (no exchange).  'x': x-slabs.
+        self._chan_rank, self._chan_world = 0, 1
+        if shard_axis == 'channel':
+            self._chan_rank, self._chan_world = int(shard[0]), int(shard[1])
+            if not (0 <= self._chan_rank < self._chan_world):
+                raise ValueError("bad (rank, world)")
             shard = (0, 1)
         self._rank, self._world = int(shard[0]), int(shard[1])
         # sharded models: ranks that receive the products as host (numpy) arrays; the others
@@ -620,7 +657,6 @@ class JetModel:
             self._dev = {"nverts": nverts, "cells": cells, "bricks": bricks,
                          "extents": extents, "model": m, "layout": (nxs, self._ny, self._nz),
                          "device": dev, "stream2": torch.cuda.Stream(device=dev),
-                         "cursor": torch.zeros(4, dtype=torch.int32, device=dev),
                          "n_ties": None, "n_patched": 0,
                          "tie_pending": (pin, ev, tb, tie_cap)}
             self._apply_overrides()
@@ -707,12 +743,35 @@ class JetModel:
         d["ray_meta"] = None
 
     def _n_active(self):
-        """Number of jet-crossing rays of the slab on the HOST (blocks; only the sharded
-        exchange and diagnostics need it)."""
+        """Number of jet-crossing rays of the slab on the HOST (blocks until the ray list is
+        built)."""
         d = self._ensure_filled()
         if d["n_active_host"] is None:
             d["n_active_host"] = int(d["n_active_dev"].item())
+            if len(_N_ACTIVE) > 256:
+                _N_ACTIVE.clear()
+            _N_ACTIVE[self._geometry_key()] = d["n_active_host"]
         return d["n_active_host"]
+
+    def _geometry_key(self):
+        g = self._params["geometry"]
+        return (self._nx, self._ny, self._nz, self._x_lo, self._x_hi, float(self._csize),
+                float(g["inc"]), float(g["pa"]), float(g["w_0"]), float(g["r_0"]),
+                float(g["mod_r_0"]), float(g["epsilon"]))
+
+    def _n_active_hint(self):
+        """Grid size of the line kernel (one CTA per jet-crossing ray is fastest).  The count is
+        a pure function of the geometry and the grid, so it is remembered per geometry: the
+        first model of a geometry reads it back once, later ones (time series, repeated runs)
+        never wait for the device.  The kernel itself reads the true count on the device, so a
+        stale hint could only cost time, not correctness."""
+        d = self._dev
+        if d["n_active_host"] is not None:
+            return d["n_active_host"]
+        if self._overrides:            # user grids may empty cells: do not trust the cache
+            return self._n_active()
+        hit = _N_ACTIVE.get(self._geometry_key())
+        return hit if hit is not None else self._n_active()
 
     def _decide_ties(self, I, J, K, dec):
         """{flat slab cell index: change of its vertex count} from the reference's own numpy
@@ -1003,12 +1062,20 @@ class JetModel:
             if line is None:
                 st = lib.rjp_integrate(d["model"], ep, ct, d["cells"].data_ptr(),
                                        d["extents"].data_ptr(), d["rays"].data_ptr(),
-                                       d["n_active_dev"].data_ptr(), d["cursor"].data_ptr(),
+                                       d["n_active_dev"].data_ptr(), 0,
                                        em.data_ptr(), kff.data_ptr(),
                                        tsum.data_ptr(), cnt.data_ptr(), None, None, 0, 1,
                                        None, None, 0, 0, self._stream(), None)
             else:
-                ln, chans, keep = self._line_structs(line, freqs, dev)
+                c_lo, c_hi = 0, len(freqs)
+                dn_all = None
+                if self._chan_world > 1:
+                    from .sharding import chan_bounds
+                    c_lo, c_hi = chan_bounds(len(freqs), self._chan_rank, self._chan_world)
+                    all_f = np.asarray(freqs, np.float64)
+                    dn_all = float(np.max(np.abs(all_f - hm.rrl_nu_0(*hm.rrl_parser(line)))))
+                    freqs = all_f[c_lo:c_hi]
+                ln, chans, keep = self._line_structs(line, freqs, dev, dn_max=dn_all)
                 nch = len(freqs)
                 # sharded: every rank writes its slab straight into full-size cubes; the
                 # other slabs arrive through the sparse exchange below
@@ -1019,14 +1086,16 @@ class JetModel:
                 if want_flux:
                     flux = torch.empty((nch, rows, nz), dtype=torch.float64, device=dev)
                 side = self._fill_remote_constants(tau, flux) if self._world > 1 else None
+                lines = nch > 0       # (more ranks than channels: continuum sums only)
                 st = lib.rjp_integrate(d["model"], ep, ct, d["cells"].data_ptr(),
                                        d["extents"].data_ptr(), d["rays"].data_ptr(),
-                                       d["n_active_dev"].data_ptr(), d["cursor"].data_ptr(),
+                                       d["n_active_dev"].data_ptr(), self._n_active_hint(),
                                        em.data_ptr(), kff.data_ptr(),
-                                       tsum.data_ptr(), cnt.data_ptr(), ln,
-                                       chans, nch, 1 if contsub else 0,
-                                       tau.data_ptr() if want_tau else None,
-                                       flux.data_ptr() if want_flux else None,
+                                       tsum.data_ptr(), cnt.data_ptr(),
+                                       ln if lines else None, chans if lines else None,
+                                       nch, 1 if contsub else 0,
+                                       tau.data_ptr() if (want_tau and lines) else None,
+                                       flux.data_ptr() if (want_flux and lines) else None,
                                        plane, coff,
                                        self._stream(), d["stream2"].cuda_stream)
                 if self._world > 1:
@@ -1037,21 +1106,21 @@ class JetModel:
             _launched(2 if line is None else 1 + (len(freqs) + 2047) // 2048)
         self._cont = {"key": key_c, "em": em, "kff": kff, "tsum": tsum, "cnt": cnt}
         if line is not None:
-            self._line = {"key": key_l, "tau": tau, "flux": flux}
+            self._line = {"key": key_l, "tau": tau, "flux": flux, "c_lo": c_lo, "c_hi": c_hi}
         if self._validate_fill():
             # a host-resolved near-tie changed a vertex count after this pass was queued:
             # the state has been patched, integrate again
             return self._pass(line, freqs, contsub, want_tau, want_flux)
         return self._cont if line is None else self._line
 
-    def _line_structs(self, line, freqs, dev):
+    def _line_structs(self, line, freqs, dev, dn_max=None):
         """Host scalars of the LTE line opacity (classes.py:1159-1169; rrls.py) and the
         per-channel device arrays.  Cached per (line, channels, model constants, device): the
         Gaunt-factor fits and the host->device copy would otherwise sit between the kernel
         launches of every pass."""
         torch = _torch()
         freqs = np.asarray(freqs, dtype=np.float64)
-        key = (line, freqs.tobytes(), str(dev), float(self._csize),
+        key = (line, freqs.tobytes(), dn_max, str(dev), float(self._csize),
                float(self._params["target"]["dist"]),
                float(self._params['properties']['T_0']),
                float(self._params['power_laws']['q_T']))
@@ -1072,7 +1141,10 @@ class JetModel:
                           np.sqrt(np.pi))
         ln.en_over_k = float(z ** 2. * hm.energy_n(n, element) / hm.k_cgs)
         ln.h_over_k = float(hm.h_cgs / hm.k_cgs)
-        ln.dn_max = float(np.max(np.abs(freqs - nu0))) if freqs.size else 0.0
+        # (a rank of a channel-sharded cube passes the maximum over ALL channels, so that
+        # every rank classifies a cell the same way)
+        ln.dn_max = dn_max if dn_max is not None else \
+            (float(np.max(np.abs(freqs - nu0))) if freqs.size else 0.0)
         # equally spaced channels (ContinuumRun.chan_freqs, classes.py:1893-1900): the kernels
         # form the offsets on the fly instead of reading them
         ln.chan_dnu0, ln.chan_step = float(freqs[0] - nu0) if freqs.size else 0.0, 0.0
@@ -1111,6 +1183,115 @@ class JetModel:
             t = gather_x(t, self._nx, self._rank, self._world, dim=0 if lead is None else 1,
                          bounds=self._bounds)
         return _to_host(t) if wanted else None
+
+    def _host_cube(self, cube, fill, nch):
+        """Device cube of a line pass -> numpy (nch, nx, nz) on the host.
+
+        One GPU: `_handover` into a pinned array.  Channel-sharded (`shard_axis='channel'`):
+        every rank hands ITS planes over ITS PCIe link into one host array in shared memory
+        (`_shared_cube`), which the host ranks return; nothing travels between GPUs.
+        x-slabs: the cube was completed on the device by the sparse exchange, plain copy."""
+        torch = _torch()
+        nxs, nz = self._x_hi - self._x_lo, self._nz
+        plane = nxs * nz
+        wanted = self._host_ranks is None or self._rank in self._host_ranks
+        if self._chan_world > 1:
+            return self._shared_cube(cube, fill, nch)
+        if self._world > 1 or cube.numel() != nch * plane:
+            return self._host_image(cube, lead=nch)
+        out = torch.empty((nch, plane), dtype=torch.float64, pin_memory=True)
+        self._handover(cube.view(nch, plane), fill, out)
+        return out.view(nch, nxs, nz).numpy() if wanted else None
+
+    def _handover(self, cube, fill, out):
+        """cube (n, plane) on the device -> out (n, plane), a page-locked host tensor.
+
+        The dense cube is mostly the constant `fill` (tau: 0, flux: NaN -- the rays that miss the
+        jet), so the host array is produced by two engines at once: host threads write the
+        constants of the first `a` planes with streaming stores and drop in the packed columns
+        of the jet-crossing rays (rjp_pack_rays -> pinned copy -> rjp_host_assemble), while the
+        copy engine moves the other planes as they are.  `a` follows the measured rates of the
+        two, so that both finish together; the result is bit-identical to the plain copy."""
+        torch = _torch()
+        lib = _cabi.load()
+        d = self._dev
+        dev = d["device"]
+        nch, plane = cube.shape
+        if nch == 0:
+            return
+        frac = os.environ.get("RAJEPY_B200_HOST_SPLIT")
+        n = self._n_active()
+        if plane % 2 or n == 0 or n > 0.3 * plane:   # (a jet that covers the sky: nothing to gain)
+            split = 0.0
+        elif frac is not None:
+            split = max(0.0, min(1.0, float(frac)))
+        elif _HANDOVER["cpu_gbs"] and _HANDOVER["dma_gbs"]:
+            split = _HANDOVER["cpu_gbs"] / (_HANDOVER["cpu_gbs"] + _HANDOVER["dma_gbs"])
+        else:
+            split = 0.5
+        a = max(0, min(nch, int(round(nch * split))))
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            ev_cols = torch.cuda.Event()
+            if a > 0:
+                if d.get("rays_host") is None:
+                    ids_h = torch.empty(n, dtype=torch.int32, pin_memory=True)
+                    ids_h.copy_(d["rays"][:n], non_blocking=True)
+                    d["rays_host"] = ids_h
+                cols = torch.empty((a, n), dtype=torch.float64, device=dev)
+                _cabi.check(lib.rjp_pack_rays(cube.data_ptr(), plane, d["rays"].data_ptr(), n, n,
+                                              a, cols.data_ptr(), stream.cuda_stream),
+                            "rjp_pack_rays")
+                _launched()
+                cols_h = torch.empty((a, n), dtype=torch.float64, pin_memory=True)
+                cols_h.copy_(cols, non_blocking=True)
+            ev_cols.record(stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            if a < nch:
+                out[a:].copy_(cube[a:], non_blocking=True)
+            e1.record(stream)
+            t_cpu = 0.0
+            if a > 0:
+                ev_cols.synchronize()
+                t0 = _time.perf_counter()
+                st = lib.rjp_host_assemble(out.data_ptr(), a, plane, d["rays_host"].data_ptr(), n,
+                                           cols_h.data_ptr(), n, float(fill), _host_threads())
+                _cabi.check(st, "rjp_host_assemble")
+                t_cpu = _time.perf_counter() - t0
+            stream.synchronize()
+            # rates for the next split (both engines were running at the same time)
+            if a > 0 and t_cpu > 0:
+                r = a * plane * 8 / t_cpu / 1e9
+                _HANDOVER["cpu_gbs"] = r if not _HANDOVER["cpu_gbs"] else \
+                    0.5 * (r + _HANDOVER["cpu_gbs"])
+            if a < nch:
+                ms = e0.elapsed_time(e1)
+                if ms > 0:
+                    r = (nch - a) * plane * 8 / (ms * 1e-3) / 1e9
+                    _HANDOVER["dma_gbs"] = r if not _HANDOVER["dma_gbs"] else \
+                        0.5 * (r + _HANDOVER["dma_gbs"])
+
+    def _shared_cube(self, cube, fill, nch):
+        """Channel-sharded hand-over: (nch, nx, nz) float64 in POSIX shared memory, every rank
+        writing the planes it integrated (collective over the default process group).  The
+        host ranks get the array, the others None."""
+        import torch.distributed as dist
+        from . import hostshare
+        from .sharding import chan_bounds
+        torch = _torch()
+        plane = self._nx * self._nz
+        c_lo, c_hi = chan_bounds(nch, self._chan_rank, self._chan_world)
+        seg = hostshare.segment(nch * plane * 8, self._chan_rank)
+        mine = seg.tensor(c_lo * plane * 8, (c_hi - c_lo, plane))     # page-locked view
+        if c_hi > c_lo:
+            self._handover(cube.view(c_hi - c_lo, plane), fill, mine)
+        dist.barrier()
+        wanted = self._host_ranks is None or self._chan_rank in self._host_ranks
+        if not wanted:
+            seg.release()
+            return None
+        return seg.array((nch, self._nx, self._nz))
 
     def _continuum_images_device(self, freqs, want):
         """K5 for a list of frequencies; `want` in ('tau', 'intensity', 'flux').
@@ -1200,8 +1381,12 @@ class JetModel:
             out["tau_ff"] = conv(self._continuum_images_device(cont_freqs, 'tau'), lead=nf)
             out["flux_ff"] = conv(self._continuum_images_device(cont_freqs, 'flux'), lead=nf)
         if line is not None:
-            out["tau_rrl"] = conv(res["tau"], lead=nch)
-            out["flux_rrl"] = conv(res["flux"], lead=nch)
+            if host:
+                out["tau_rrl"] = self._host_cube(res["tau"], 0.0, nch)
+                out["flux_rrl"] = self._host_cube(res["flux"], float("nan"), nch)
+            else:
+                out["tau_rrl"] = conv(res["tau"], lead=nch)
+                out["flux_rrl"] = conv(res["flux"], lead=nch)
         return out
 
     def _ray_meta(self):
@@ -1351,7 +1536,7 @@ class JetModel:
             return tau[0] if scalar else tau
         res = self._pass(rrl, freqs, contsub=self._line_contsub_hint(), want_tau=True,
                          want_flux=True)
-        tau = self._host_image(res["tau"], lead=freqs.size)
+        tau = self._host_cube(res["tau"], 0.0, freqs.size)
         if tau is None:
             return None
         if scalar:
@@ -1372,7 +1557,7 @@ class JetModel:
         scalar = np.isscalar(freq)
         freqs = np.atleast_1d(np.asarray(freq, dtype=np.float64))
         res = self._pass(rrl, freqs, contsub=True, want_tau=True, want_flux=True)
-        ints = self._host_image(res["flux"], lead=freqs.size)
+        ints = self._host_cube(res["flux"], float("nan"), freqs.size)
         if ints is None:
             return None
         ints = ints * (1e-26 / self._pixel_solid_angle())
@@ -1389,7 +1574,7 @@ class JetModel:
         scalar = np.isscalar(freq)
         freqs = np.atleast_1d(np.asarray(freq, dtype=np.float64))
         res = self._pass(rrl, freqs, contsub=contsub, want_tau=True, want_flux=True)
-        fluxes = self._host_image(res["flux"], lead=freqs.size)
+        fluxes = self._host_cube(res["flux"], float("nan"), freqs.size)
         if fluxes is None:
             return None
         if scalar:

@@ -22,6 +22,16 @@ class Entry:
         self.message = entry
         self.rtime = time.localtime() if timestamp else None
 
+    def __setstate__(self, state):
+        # entries pickled by the reference (logger/logger.py:180-209) carry _mtype / _message /
+        # _mtime / timestamp
+        if '_message' in state:
+            self.mtype = str(state.get('_mtype', 'INFO')).upper()
+            self.message = state['_message']
+            self.rtime = state.get('_mtime') if state.get('timestamp', True) else None
+        else:
+            self.__dict__.update(state)
+
     def __str__(self):
         stamp = time.strftime("%d%b%Y-%H:%M:%S", self.rtime).upper() if self.rtime else ""
         pre = "::".join([s for s in (stamp, self.mtype.ljust(7)) if s])
@@ -36,6 +46,11 @@ class Log:
         dcy = os.path.dirname(os.path.abspath(fname))
         if not os.path.isdir(dcy):
             raise FileNotFoundError(f"{dcy} is not a directory")
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        if isinstance(self._entries, dict):     # the reference numbers its entries in a dict
+            self._entries = [self._entries[k] for k in sorted(self._entries)]
 
     def __str__(self):
         return "\n".join(str(e) for e in self._entries)

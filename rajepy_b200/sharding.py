@@ -57,6 +57,38 @@ def epoch_shares(n_epochs, rank, world):
     return list(range(rank, n_epochs, world))
 
 
+def chan_bounds(nchan, rank, world):
+    """[c_lo, c_hi) of the channels `rank` integrates when a line cube is sharded by CHANNEL:
+    contiguous blocks (a block of channel planes is a contiguous piece of the (nchan, nx, nz)
+    cube, i.e. of the FITS product), as even as possible.  Every rank walks all jet-crossing
+    rays for its channels and writes only its planes: no exchange of cube data at all."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad (rank, world)")
+    base, extra = divmod(int(nchan), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_channel_totals(local, nchan, rank, world, group=None):
+    """All-gather per-channel scalars (e.g. the sky-summed flux of every channel, what
+    Pipeline stores as results['flux'], classes.py:2468-2472) of a channel-sharded cube:
+    `local` holds the values of chan_bounds(nchan, rank, world); returns (nchan,) on every rank."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return local
+    nmax = (nchan + world - 1) // world
+    pad = torch.zeros(nmax, dtype=local.dtype, device=local.device)
+    pad[:local.numel()] = local
+    buf = torch.empty(world * nmax, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    parts = []
+    for r in range(world):
+        lo, hi = chan_bounds(nchan, r, world)
+        parts.append(buf[r * nmax: r * nmax + (hi - lo)])
+    return torch.cat(parts)
+
+
 def gather_epochs(local, n_epochs, rank, world, group=None):
     """All-gather per-epoch results of a time series whose epochs were dealt round-robin
     (`epoch_shares`): `local` is (len(epoch_shares(n_epochs, rank, world)), ...) in the order of

@@ -129,3 +129,27 @@ BIG_CASES = {
              {"pick": lambda: (np.array(_BENCH_PICK) - 255.5) * 1e5,
               "uni": lambda: (np.arange(8) - 3.5) * 4e5}, ("uni",), 3),
 }
+
+
+def pipeline_case():
+    """(model params, pipeline params) of the Pipeline-glue fixtures
+    (tools/make_golden_pipeline.py): a tiny grid, two epochs x two continuum bands (one with
+    3 channels), one epoch x one RRL with 6 channels."""
+    model = with_grid(base_params(), 12, 16, 28)
+    pline = {'min_el': 20.,
+             'dcys': {"model_dcy": "pl"},
+             'continuum': {'times': np.array([1.0, 0.25]),
+                           'freqs': np.array([5., 43.]) * 1e9,
+                           't_obs': np.array([1200, 1200]),
+                           'tscps': np.array([('VLA', 'A'), ('VLA', 'B')]),
+                           't_ints': np.array([5, 5]),
+                           'bws': np.array([.6e9, 1e9]),
+                           'chanws': np.array([2.e8, 1.e9])},
+             'rrls': {'times': np.array([1.0]),
+                      'lines': np.array(['H58a']),
+                      't_obs': np.array([3000]),
+                      'tscps': np.array([('VLA', 'A')]),
+                      't_ints': np.array([60]),
+                      'bws': np.array([6e6]),
+                      'chanws': np.array([1e6])}}
+    return model, pline

@@ -27,7 +27,7 @@ def test_sparse_walk_equals_dense_sweep(name):
     em, kff, tsum = (torch.empty(npix, dtype=torch.float64, device="cuda") for _ in range(3))
     cnt = torch.empty(npix, dtype=torch.int32, device="cuda")
     st = lib.rjp_integrate(d["model"], jm._epoch_struct(), jm._continuum_struct(),
-                           d["cells"].data_ptr(), None, None, None, None, em.data_ptr(),
+                           d["cells"].data_ptr(), None, None, None, 0, em.data_ptr(),
                            kff.data_ptr(),
                            tsum.data_ptr(), cnt.data_ptr(), None, None, 0, 1, None, None,
                            0, 0, jm._stream(), None)

@@ -75,11 +75,13 @@ def double_to_float_trunc(v):
 
 def core_threshold(y, t):
     """X^2 below which a cell of Lorentz ratio y takes the core path: the larger of the
-    wing polynomials' validity limit and the point where exp(-x^2) < 1e-8 K (make_fast_entry)."""
-    x2 = 28.0
-    for _ in range(3):
-        x2 = np.log(1e8 * np.sqrt(np.pi) * x2 / y)
-    return float(min(max(t["xwing2"], x2 * t["kappa"] ** 2), t["xcore2"] - 0.01))
+    wing polynomials' validity limit and the point where exp(-x^2) < 1e-8 K
+    (vt_cell_constants: fp32 logs, nudged to the safe side)."""
+    lc = f32(np.log(f32(1e8) * f32(1.7724538509055159) / f32(y))) + f32(1e-3)
+    x2 = lc + f32(3.3322045)
+    for _ in range(2):
+        x2 = lc + f32(np.log(x2))
+    return float(min(max(t["xwing2"], float(x2) * t["kappa"] ** 2), t["xcore2"] - 0.01))
 
 
 def cell_constants(y, t):
@@ -133,10 +135,10 @@ def voigt_fast(x, y, t=None):
     T = cc["yy"] - Xc * Xc
     i_ = np.rint(T)
     f = T - i_
-    p = np.full_like(f, t["exp2"][-1])
-    for c in t["exp2"][-2::-1]:
-        p = p * f + c
-    Gf = double_to_float_trunc(np.ldexp(p, i_.astype(np.int64)))
+    # device: 2^f by MUFU.EX2 on float(f) (<= 2 ulp of fp32; emulated as the correctly rounded
+    # value), the integer part added to the exponent field
+    Gf = f32(np.ldexp(np.exp2(f.astype(f32).astype(np.float64)).astype(f32).astype(np.float64),
+                      i_.astype(np.int64)))
     Xf = mulf(q.astype(f32), f32(2.0 ** -25))
     a = mulf(Xf, cc["ya"])
     a2 = mulf(a, a)

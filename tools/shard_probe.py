@@ -64,7 +64,7 @@ def main():
         jm._pass(line, chans, contsub=False)
         torch.cuda.synchronize()
     t0 = marks[0][1]
-    txt = f"rank {rank}: n_active={jm._dev['n_active']} " + ", ".join(
+    txt = f"rank {rank}: n_active={jm._n_active()} " + ", ".join(
         f"{n} @ {t0.elapsed_time(e):.2f} ms" for n, e in marks)
     txt += f", side stream fills done @ {t0.elapsed_time(side_marks[0]):.2f} ms, slab {jm.slab}"
     print(txt, file=sys.stderr, flush=True)
