@@ -114,6 +114,13 @@ typedef struct {
   double dn_max;        /* max_k |nu_k - nu0| [Hz] over the channels of this call  */
   double chan_dnu0;     /* equally spaced channels: dnu[k] = chan_dnu0 + k * chan_step     */
   double chan_step;     /* [Hz]; 0 = not equally spaced (the kernels then read dnu[])      */
+  /* functions of the temperature alone, precomputed for the temperature most cells have
+   * (isothermal jets, q_T = q^d_T = 0); t_common = 0: none, the kernels evaluate them per cell */
+  double t_common;      /* [K]                                                             */
+  double tc_sqrt;       /* sqrt(t_common)                                                  */
+  double tc_boltz;      /* exp(en_over_k / t_common)                                       */
+  double tc_hk;         /* h_over_k / t_common                                             */
+  double tc_p0;         /* 1 - exp(-tc_hk * nu0)                                           */
 } rjp_line;
 
 /* Per-channel host-prepared scalars, each a DEVICE array of nchan doubles. */

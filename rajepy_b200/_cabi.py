@@ -48,7 +48,8 @@ class Continuum(C.Structure):
 class Line(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("nu0", "dopp", "width_g", "stark", "kappa0",
                                           "en_over_k", "h_over_k", "dn_max", "chan_dnu0",
-                                          "chan_step")]
+                                          "chan_step", "t_common", "tc_sqrt", "tc_boltz",
+                                          "tc_hk", "tc_p0")]
 
 
 class Channels(C.Structure):

@@ -495,7 +495,7 @@ __device__ __forceinline__ float vt_core(const FastEntry& e, uint32_t tab, doubl
   const uint32_t row = tab + (uint32_t)(q >> 24) * (RJP_VT_ROW * 4);
   const float t = fmaf(__int2float_rn(q & 0xFFFFFF), 1.1920928955078125e-07f, -1.0f);
   const float4 r0 = lds_f4(row), r1 = lds_f4(row + 16), r2 = lds_f4(row + 32),
-               r3 = lds_f4(row + 48), r4 = lds_f4(row + 64);
+               r3 = lds_f4(row + 48);
   float a = fmaf(r1.w, t, r1.z);
   a = fmaf(a, t, r1.y);
   a = fmaf(a, t, r1.x);
@@ -508,6 +508,7 @@ __device__ __forceinline__ float vt_core(const FastEntry& e, uint32_t tab, doubl
   b = fmaf(b, t, r2.z);
   b = fmaf(b, t, r2.y);
   b = fmaf(b, t, r2.x);
+  const float4 r4 = lds_f4(row + 64);
   float c = fmaf(r4.y, t, r4.x);
   c = fmaf(c, t, r3.w);
   c = fmaf(c, t, r3.z);

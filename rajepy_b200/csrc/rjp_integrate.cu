@@ -71,7 +71,7 @@ struct LineEntry {   // channel-independent factors of one in-jet cell (rrls.py:
   double hk;         // h / (k T); negative: |hk * dn| is small for every channel, use a1..a3
   double a1, a2;     // 1 - exp(-h nu/kT) = p0 + dn (a1 + dn (a2 + dn a3)) + O((hk dn)^4)
   double a3;
-  double pad;
+  double pad;        // 1: the quadratic term of that polynomial is negligible (fast class)
 };
 
 __device__ __forceinline__ double2 ld_cell(const double2* p) {
@@ -275,22 +275,34 @@ __device__ __noinline__ LineEntry make_entry(const Decoded& d, const rjp_model& 
   const double vlos = velocity_of(m, centroid_rw(m, ix, iy, iz)).vlos_rel + m.v_lsr;
   const double shift = -ln.nu0 * (vlos * ln.dopp);           // nu0_cell - nu0 (physics.py:558)
   const double nu0c = ln.nu0 + shift;
-  const double s2 = ln.width_g * sqrt(d.temp) * nu0c;        // sigma*sqrt2 (rrls.py:104-118, :349)
+  // functions of the temperature alone: precomputed on the host for the temperature most
+  // cells have (a jet with q_T = q^d_T = 0 is isothermal: every BASELINE configuration)
+  double sqt, boltz;
+  if (d.temp == ln.t_common) {
+    sqt = ln.tc_sqrt;
+    boltz = ln.tc_boltz;
+    e.hk = ln.tc_hk;
+    e.p0 = ln.tc_p0;
+  } else {
+    sqt = sqrt(d.temp);
+    boltz = exp(ln.en_over_k / d.temp);
+    e.hk = ln.h_over_k / d.temp;
+    e.p0 = -expm1(-e.hk * ln.nu0);
+  }
+  const double s2 = ln.width_g * sqt * nu0c;                 // sigma*sqrt2 (rrls.py:104-118, :349)
   e.inv_s2 = 1.0 / s2;
   e.xs = -shift * e.inv_s2;
   e.y = ln.stark * d.ne * e.inv_s2;                          // rrls.py:101, :353
-  e.hk = ln.h_over_k / d.temp;
-  e.p0 = -expm1(-e.hk * ln.nu0);
   // Taylor coefficients of (1 - p0)(1 - exp(-hk dn)) in dn; used when |hk dn| <= 1e-3
   // for all channels (error <= (1e-3)^4 / 24 relative), see planck_factor()
   e.a1 = (1.0 - e.p0) * e.hk;
   e.a2 = -0.5 * e.a1 * e.hk;
   e.a3 = (1.0 / 6.0) * e.a1 * e.hk * e.hk;
-  e.pad = 0.0;
+  // the fast class keeps only the linear term: its quadratic one must be < 1e-9 of p0
+  e.pad = (fabs(e.a2) * dn_max * dn_max <= 1e-9 * e.p0) ? 1.0 : 0.0;
   if (e.hk * dn_max <= 1e-3) e.hk = -e.hk;
   // rrls.py:383-389 with n_i = (X mu'/m_amu) n_e, times path length and 1/(sigma sqrt(2 pi))
-  e.amp = ln.kappa0 * d.ne * d.ne * d.ffw / (d.temp * sqrt(d.temp)) *
-          exp(ln.en_over_k / d.temp) * e.inv_s2;
+  e.amp = ln.kappa0 * d.ne * d.ne * d.ffw / (d.temp * sqt) * boltz * e.inv_s2;
   // NaN velocity / density / temperature: the reference's nansum drops the cell
   if (!(vlos == vlos) || !d.ne_ok || !d.t_ok || !(e.amp == e.amp)) e.amp = 0.0;
   return e;
@@ -299,7 +311,8 @@ __device__ __noinline__ LineEntry make_entry(const Decoded& d, const rjp_model& 
 // Fast class (rjp_device.cuh, "mixed-precision Voigt"): small Lorentz/Gauss ratio and a
 // Planck factor that is a short polynomial in the channel offset.
 __device__ __forceinline__ bool fast_class(const LineEntry& e) {
-  return e.amp != 0.0 && e.hk < 0.0 && e.y >= RJP_VT_Y_MIN && e.y <= RJP_VT_Y_MAX;
+  return e.amp != 0.0 && e.hk < 0.0 && e.pad != 0.0 && e.y >= RJP_VT_Y_MIN &&
+         e.y <= RJP_VT_Y_MAX;
 }
 
 __device__ __noinline__ FastEntry to_fast(const LineEntry& s) {
@@ -310,7 +323,7 @@ __device__ __noinline__ FastEntry to_fast(const LineEntry& s) {
   e.a0 = s.amp * s.p0;
   e.w0 = e.a0 * s.y * (RJP_VT_KAPPA * RJP_VT_KAPPA * RJP_VT_G10);
   e.b1 = (float)(s.a1 / s.p0);
-  e.b2 = (float)(s.a2 / s.p0);
+  e.b2 = 0.0f;
   return e;
 }
 
@@ -618,6 +631,67 @@ ray_compact_kernel(const int2* __restrict__ extents, int nray,
   }
 }
 
+// Phase 2a of the channel loop: the fast-class cells [i0, i1) of the batch added to this
+// thread's GCH channels.  The wing term is evaluated branch-free for all channels (8
+// independent chains per thread); channels inside the Gaussian core replace it by the table
+// evaluation.  (A second copy of this loop specialised for y <= 0.03 -- no y^5 term, shorter
+// cosine: 7 instructions less per core evaluation, 4.61 instead of 4.79 ms when used for every
+// cell -- made the kernel SLOWER when both copies were present, 4.87 ms: the loop body is
+// 10 KB of code and the instruction cache does not hold two of them.)
+template <bool UNI, int GCH>
+__device__ __forceinline__ void fast_cells(const FastEntry* __restrict__ s_fast, int i0, int i1,
+                                           double (&acc)[GCH], const double* dn,
+                                           const f32x2* dnf2, double dstep, float dstepf,
+                                           uint32_t tab) {
+  for (int i = i0; i < i1; ++i) {
+    const FastEntry fe = s_fast[i];
+    const WingCoef2 wc = vt_wing_coef2(fe);
+    const f32x2 b1 = pk2(fe.b1, fe.b1);
+    const double X0 = fma(dn[0], fe.inv, fe.xs), dX = dstep * fe.inv;   // UNI only
+#pragma unroll
+    for (int j = 0; j < GCH; j += 2) {
+      // two channels per step: the fp32 work runs as packed FFMA2
+      double Xa, Xb;
+      if constexpr (UNI) {
+        Xa = fma((double)j, dX, X0);
+        Xb = fma((double)(j + 1), dX, X0);
+      } else {
+        Xa = fma(dn[j], fe.inv, fe.xs);
+        Xb = fma(dn[j + 1], fe.inv, fe.xs);
+      }
+      const double X2a = Xa * Xa, X2b = Xb * Xb;
+      const bool corea = __double2hiint(X2a) < fe.xc2_hi, coreb = __double2hiint(X2b) < fe.xc2_hi;
+      const double ra = rcp_seed(X2a), rb = rcp_seed(X2b);
+      double leada = fe.w0 * (ra * fma(-X2a, ra, 2.0));
+      double leadb = fe.w0 * (rb * fma(-X2b, rb, 2.0));
+      f32x2 k2 = vt_wing_poly2(wc, pk2(d2f_trunc_pos(ra), d2f_trunc_pos(rb)));
+      if (corea || coreb) {
+        float ka, kb;
+        upk2(k2, ka, kb);
+        if (corea) {
+          ka = vt_core(fe, tab, Xa, X2a);
+          leada = fe.a0;
+        }
+        if (coreb) {
+          kb = vt_core(fe, tab, Xb, X2b);
+          leadb = fe.a0;
+        }
+        k2 = pk2(ka, kb);
+      }
+      f32x2 d2;
+      if constexpr (UNI)
+        d2 = fma2(pk2((float)j, (float)(j + 1)), pk2(dstepf, dstepf), dnf2[0]);
+      else
+        d2 = dnf2[j >> 1];
+      // (1 - exp(-h nu / kT)) / p0 = 1 + dn b1 (fast class: the next term is < 1e-9)
+      float ka, kb;
+      upk2(fma2(k2, mul2(d2, b1), k2), ka, kb);
+      acc[j] = fma(leada, f2d_pos(ka), acc[j]);
+      acc[j + 1] = fma(leadb, f2d_pos(kb), acc[j + 1]);
+    }
+  }
+}
+
 // UNI: the channels are equally spaced (rjp_line.chan_step != 0): the channel offsets are
 // formed on the fly from two per-thread scalars instead of living in 24 registers (16 of
 // which spilled), which is what lets the kernel fit more warps per SM.
@@ -748,56 +822,8 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
     }
     __syncthreads();
 
-    // phase 2a, fast class: every thread adds each prepared cell to its GCH channels.  The
-    // wing term is evaluated branch-free for all channels (8 independent chains per
-    // thread); channels inside the Gaussian core replace it by the table evaluation.
-    for (int i = 0; i < nf; ++i) {
-      const FastEntry fe = s_fast[i];
-      const WingCoef2 wc = vt_wing_coef2(fe);
-      const f32x2 b1 = pk2(fe.b1, fe.b1), b2 = pk2(fe.b2, fe.b2);
-      const double X0 = fma(dn[0], fe.inv, fe.xs), dX = dstep * fe.inv;   // UNI only
-#pragma unroll
-      for (int j = 0; j < GCH; j += 2) {
-        // two channels per step: the fp32 work runs as packed FFMA2
-        double Xa, Xb;
-        if constexpr (UNI) {
-          Xa = fma((double)j, dX, X0);
-          Xb = fma((double)(j + 1), dX, X0);
-        } else {
-          Xa = fma(dn[j], fe.inv, fe.xs);
-          Xb = fma(dn[j + 1], fe.inv, fe.xs);
-        }
-        const double X2a = Xa * Xa, X2b = Xb * Xb;
-        const bool corea = __double2hiint(X2a) < fe.xc2_hi, coreb = __double2hiint(X2b) < fe.xc2_hi;
-        const double ra = rcp_seed(X2a), rb = rcp_seed(X2b);
-        double leada = fe.w0 * (ra * fma(-X2a, ra, 2.0));
-        double leadb = fe.w0 * (rb * fma(-X2b, rb, 2.0));
-        f32x2 k2 = vt_wing_poly2(wc, pk2(d2f_trunc_pos(ra), d2f_trunc_pos(rb)));
-        if (corea || coreb) {
-          float ka, kb;
-          upk2(k2, ka, kb);
-          if (corea) {
-            ka = vt_core(fe, tab, Xa, X2a);
-            leada = fe.a0;
-          }
-          if (coreb) {
-            kb = vt_core(fe, tab, Xb, X2b);
-            leadb = fe.a0;
-          }
-          k2 = pk2(ka, kb);
-        }
-        f32x2 d2;
-        if constexpr (UNI)
-          d2 = fma2(pk2((float)j, (float)(j + 1)), pk2(dstepf, dstepf), dnf2[0]);
-        else
-          d2 = dnf2[j >> 1];
-        const f32x2 eps = mul2(d2, fma2(d2, b2, b1));
-        float ka, kb;
-        upk2(fma2(k2, eps, k2), ka, kb);
-        acc[j] = fma(leada, f2d_pos(ka), acc[j]);
-        acc[j + 1] = fma(leadb, f2d_pos(kb), acc[j + 1]);
-      }
-    }
+    // phase 2a, fast class: every thread adds each prepared cell to its GCH channels
+    fast_cells<UNI, GCH>(s_fast, 0, nf, acc, dn, dnf2, dstep, dstepf, tab);
 
     // phase 2b, everything else in fp64 (large or tiny y, steep Planck factor): 4 cells at a
     // time, channel loop outermost
@@ -863,6 +889,11 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
 
   // K5 epilogue: rrls.py:444-447, physics.py:571-574, classes.py:1323-1328, :1484-1488
   const double tmean = ts / (double)cn;
+  // exp(h nu_c / k Tmean) = exp(h nu0 / k Tmean) exp(x), x = h (nu_c - nu0) / k Tmean: one exp
+  // per ray and a cubic when |x| <= 1e-3 for every channel (x^4 / 24 <= 4e-14)
+  const double hkm = ln.h_over_k / tmean;
+  const bool bnu_taylor = hkm * dn_max <= 1e-3;
+  const double e_nu0 = bnu_taylor ? exp(hkm * ln.nu0) : 0.0;
 #pragma unroll
   for (int j = 0; j < GCH; ++j) {
     const int c = g + j * NT;
@@ -873,7 +904,14 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
       if (cn > 0) {
         const double tc = __ldg(ch.cff + c) * kray;
         const double ec = exp(-tc);
-        const double bnu = __ldg(ch.bnu + c) / (exp(ln.h_over_k * __ldg(ch.nu + c) / tmean) - 1.0);
+        double e_nu;
+        if (bnu_taylor) {
+          const double x = hkm * (UNI ? fma((double)j, dstep, dn[0]) : dn[j]);
+          e_nu = e_nu0 * fma(x, fma(x, fma(x, 1.0 / 6.0, 0.5), 1.0), 1.0);
+        } else {
+          e_nu = exp(ln.h_over_k * __ldg(ch.nu + c) / tmean);
+        }
+        const double bnu = __ldg(ch.bnu + c) / (e_nu - 1.0);
         s = bnu * ec * (1.0 - exp(-acc[j]));
         if (!contsub) s += __ldg(ch.aff + c) * (tmean * (1.0 - ec));
       }

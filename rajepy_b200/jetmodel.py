@@ -1123,7 +1123,8 @@ class JetModel:
         key = (line, freqs.tobytes(), dn_max, str(dev), float(self._csize),
                float(self._params["target"]["dist"]),
                float(self._params['properties']['T_0']),
-               float(self._params['power_laws']['q_T']))
+               float(self._params['power_laws']['q_T']),
+               float(self._params['power_laws']['q^d_T']))
         hit = _LINE_STRUCTS.get(key)
         if hit is not None:
             return hit
@@ -1153,6 +1154,17 @@ class JetModel:
             dev_max = np.max(np.abs(freqs - (freqs[0] + step * np.arange(freqs.size))))
             if step != 0.0 and dev_max <= 1e-9 * abs(step):
                 ln.chan_step = float(step)
+        # isothermal jet (q_T = q^d_T = 0 and no assigned temperature grid: T = T_0 exactly in
+        # every cell): the temperature-only factors are formed here once
+        pl = self._params['power_laws']
+        ln.t_common = 0.0
+        if pl['q_T'] == 0. and pl['q^d_T'] == 0.:
+            t0 = float(self._params['properties']['T_0'])
+            ln.t_common = t0
+            ln.tc_sqrt = float(np.sqrt(t0))
+            ln.tc_boltz = float(np.exp(ln.en_over_k / t0))
+            ln.tc_hk = float(ln.h_over_k / t0)
+            ln.tc_p0 = float(-np.expm1(-ln.tc_hk * ln.nu0))
         omega_jy = self._pixel_solid_angle() / 1e-26
         host = np.stack([
             freqs - nu0,

@@ -98,15 +98,19 @@ def test_large_grid_properties(n, nch):
     # for optically thin edge pixels that carries an absolute noise of ~ulp(1) * prefactor
     omega = np.arctan(0.5 * con.au / (120. * con.parsec)) ** 2. / 1e-26
     pref = (2. * chans[sub] ** 2. * con.k * 1e4 / con.c ** 2. * omega)[:, None, None]
-    lim = 1e-13 * (np.abs(s_cs) + s_ff) + 32 * np.finfo(float).eps * pref
+    lim = 2e-7 * np.abs(s_cs) + 1e-13 * s_ff + 32 * np.finfo(float).eps * pref
     assert np.all(np.abs(s_all[sub] - (s_cs + s_ff))[ok] <= lim[ok])
-    # (3) how the channels are batched does not matter (only the summation order of the
-    # cells along a ray may change with the block size: a few ulp)
+    # (3) how the channels are batched does not matter beyond the fp32 part of the Voigt split:
+    # another channel count means another thread layout, the channel offsets are then formed
+    # with different roundings (1 ulp of fp64), which can flip an fp32 rounding inside single
+    # evaluations (6e-8 each; far less on the sums).  The same call twice is bit-identical.
     tau = jm.optical_depth_rrl('H58a', chans)
     half = jm.optical_depth_rrl('H58a', chans[:nch // 2])
-    np.testing.assert_allclose(tau[:nch // 2], half, rtol=1e-13, atol=0)
+    np.testing.assert_allclose(tau[:nch // 2], half, rtol=2e-7, atol=0)
     one = jm.optical_depth_rrl('H58a', float(chans[7]))
-    np.testing.assert_allclose(tau[7], one, rtol=1e-13, atol=0)
+    np.testing.assert_allclose(tau[7], one, rtol=2e-7, atol=0)
+    jm._line = None
+    assert np.array_equal(jm.optical_depth_rrl('H58a', chans), tau)
     assert tau.min() >= 0.0 and np.array_equal(tau[0] > 0, em > 0)
     del s_all, s_cs, tau, half
     jm.release()
