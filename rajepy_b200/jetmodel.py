@@ -1595,6 +1595,21 @@ class JetModel:
             self._save_image(fluxes, savefits, 'flux', freq, scalar)
         return fluxes
 
+    def rrl_flux_totals(self, rrl, freq, contsub=False, host=True):
+        """Sky-summed flux of every channel [Jy], i.e. what Pipeline stores as a line run's
+        `results['flux']` (np.nansum over both sky axes, classes.py:2468-2472), reduced on the
+        device.  Sharded models all-gather the per-channel sums (the only collective of a
+        channel-sharded run), so every rank gets all `len(freq)` values."""
+        torch = _torch()
+        freqs = np.atleast_1d(np.asarray(freq, dtype=np.float64))
+        res = self._pass(rrl, freqs, contsub=contsub, want_tau=True, want_flux=True)
+        flux = res["flux"]
+        local = torch.nansum(flux.reshape(flux.shape[0], -1), dim=1)
+        if self._chan_world > 1:
+            from .sharding import gather_channel_totals
+            local = gather_channel_totals(local, freqs.size, self._chan_rank, self._chan_world)
+        return local.cpu().numpy() if host else local
+
     def _cellwise_tau_rrl(self, rrl, freqs):
         """`optical_depth_rrl(..., collapse=False)` (classes.py:1159-1189, rrls.py:329-389):
         un-summed (nfreq, nx, ny, nz) line optical depths, composed on the host from the fp64

@@ -176,3 +176,56 @@ def test_epoch_sharded_series_is_reassembled_in_order(world, n_epochs):
     want = np.arange(6)[None, :] + 100.0 * np.arange(n_epochs)[:, None]
     for r in range(world):
         assert np.array_equal(np.load(os.path.join(tmp, f"e{r}.npy")), want)
+
+
+# ------------------------------------------------------------------ channel sharding
+def _chan_worker(rank, world, port, nchan, out_dir):
+    """Every rank owns chan_bounds(nchan, rank, world) of a synthetic cube: the all-gather of
+    the per-channel totals and the shared-memory hand-over (hostshare, without CUDA: the
+    segment is only page-locked on a GPU box) must reassemble the whole product."""
+    import torch
+    import torch.distributed as dist
+    from rajepy_b200 import hostshare, sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    plane = 6 * 10
+    cube = np.arange(nchan * plane, dtype=np.float64).reshape(nchan, plane) * 0.5
+    cube[:, ::7] = np.nan
+    lo, hi = sharding.chan_bounds(nchan, rank, world)
+    local = torch.from_numpy(cube[lo:hi].copy())
+    tot = sharding.gather_channel_totals(torch.nansum(local, dim=1), nchan, rank, world)
+    ok = np.array_equal(tot.numpy(), np.nansum(cube, axis=1))
+    for _ in range(2):                       # second round reuses the pooled segment
+        seg = hostshare.segment(nchan * plane * 8, rank)
+        seg._register = lambda: None         # no CUDA here
+        mine = seg.tensor(lo * plane * 8, (hi - lo, plane))
+        mine.copy_(local)
+        dist.barrier()
+        if rank == 0:
+            arr = seg.array((nchan, 6, 10))
+            ok = ok and np.array_equal(np.nan_to_num(arr.reshape(nchan, plane)),
+                                       np.nan_to_num(cube))
+            ok = ok and seg.busy
+            del arr
+            ok = ok and not seg.busy
+        dist.barrier()
+    open(os.path.join(out_dir, f"r{rank}.txt"), "w").write("ok" if ok else "MISMATCH")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nchan", [(2, 8), (3, 10), (4, 3)])
+def test_channel_sharding_world(world, nchan):
+    import torch.multiprocessing as mp
+    from rajepy_b200 import sharding
+    # the blocks tile [0, nchan) in order, sizes differ by at most one
+    bounds = [sharding.chan_bounds(nchan, r, world) for r in range(world)]
+    assert bounds[0][0] == 0 and bounds[-1][1] == nchan
+    assert all(bounds[i][1] == bounds[i + 1][0] for i in range(world - 1))
+    sizes = [hi - lo for lo, hi in bounds]
+    assert max(sizes) - min(sizes) <= 1
+    tmp = tempfile.mkdtemp()
+    mp.spawn(_chan_worker, args=(world, _free_port(), nchan, tmp), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(tmp, f"r{r}.txt")).read() == "ok"
