@@ -331,6 +331,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     kernel_ms = []
+    e2e_parts = []
 
     def device_step():
         """HBM-resident step: fill + fused pass + image epilogue (+ the exchange)."""
@@ -351,11 +352,16 @@ def run_gpu(args):
         """Through the public JetModel API with host (numpy) results."""
         # N > 1: the products land in rank 0's host memory (the rank that writes the FITS
         # files); with channel sharding every rank moves its planes over its own PCIe link
+        t = [time.perf_counter()]
         jm = make_model(host_ranks=(0,) if world > 1 else None)
         s_ff = jm.flux_ff(cont)
+        t.append(time.perf_counter())
         t_l = jm.optical_depth_rrl(line, chans)
+        t.append(time.perf_counter())
         s_l = jm.flux_rrl(line, chans, contsub=False)
+        t.append(time.perf_counter())
         jm.release()
+        e2e_parts.append([1e3 * (b - a) for a, b in zip(t[:-1], t[1:])])
         if s_l is None:
             return 0, 0.0
         return s_ff.nbytes + t_l.nbytes + s_l.nbytes, float(np.nansum(s_l[len(chans) // 2]))
@@ -528,6 +534,9 @@ def run_gpu(args):
                     "ms_per_step": float(e2e_s) * 1e3,
                     "pcie_bytes_per_step": None,
                     "handover_rates_gbs": handover,
+                    "ms_parts_last_step": dict(zip(
+                        ("model_fill_continuum_flux_ff", "line_pass_and_tau_cube", "flux_cube"),
+                        e2e_parts[-1])),
                     "note": "JetModel(params) -> flux_ff(16 freqs), optical_depth_rrl, "
                             "flux_rrl(contsub=False) returned as dense numpy arrays (N > 1: in "
                             "rank 0's host memory); inputs are the parameter dict (no bulk H2D "

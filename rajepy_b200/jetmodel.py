@@ -1196,7 +1196,7 @@ class JetModel:
                          bounds=self._bounds)
         return _to_host(t) if wanted else None
 
-    def _host_cube(self, cube, fill, nch):
+    def _host_cube(self, cube, fill, nch, sibling=None):
         """Device cube of a line pass -> numpy (nch, nx, nz) on the host.
 
         One GPU: `_handover` into a pinned array.  Channel-sharded (`shard_axis='channel'`):
@@ -1208,22 +1208,58 @@ class JetModel:
         plane = nxs * nz
         wanted = self._host_ranks is None or self._rank in self._host_ranks
         if self._chan_world > 1:
-            return self._shared_cube(cube, fill, nch)
+            return self._shared_cube(cube, fill, nch, sibling)
         if self._world > 1 or cube.numel() != nch * plane:
             return self._host_image(cube, lead=nch)
         out = torch.empty((nch, plane), dtype=torch.float64, pin_memory=True)
-        self._handover(cube.view(nch, plane), fill, out)
+        self._handover(cube.view(nch, plane), fill, out,
+                       None if sibling is None else sibling.view(nch, plane))
         return out.view(nch, nxs, nz).numpy() if wanted else None
 
-    def _handover(self, cube, fill, out):
+    def _stage_columns(self, cube):
+        """Queue (asynchronously) the packed columns of the jet-crossing rays of `cube`
+        (n, plane) for the host: rjp_pack_rays -> copy into page-locked memory.  Returns
+        (host columns, event); staged once per cube of the current line pass."""
+        torch = _torch()
+        lib = _cabi.load()
+        d = self._dev
+        dev = d["device"]
+        staged = self._line.setdefault("staged", {}) if self._line is not None else {}
+        hit = staged.get(cube.data_ptr())
+        if hit is not None:
+            return hit
+        nch, plane = cube.shape
+        n = self._n_active()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            if d.get("rays_host") is None:
+                ids_h = torch.empty(n, dtype=torch.int32, pin_memory=True)
+                ids_h.copy_(d["rays"][:n], non_blocking=True)
+                d["rays_host"] = ids_h
+            cols = torch.empty((nch, n), dtype=torch.float64, device=dev)
+            _cabi.check(lib.rjp_pack_rays(cube.data_ptr(), plane, d["rays"].data_ptr(), n, n,
+                                          nch, cols.data_ptr(), stream.cuda_stream),
+                        "rjp_pack_rays")
+            _launched()
+            cols_h = torch.empty((nch, n), dtype=torch.float64, pin_memory=True)
+            cols_h.copy_(cols, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        staged[cube.data_ptr()] = (cols_h, ev)
+        return cols_h, ev
+
+    def _handover(self, cube, fill, out, sibling=None):
         """cube (n, plane) on the device -> out (n, plane), a page-locked host tensor.
 
         The dense cube is mostly the constant `fill` (tau: 0, flux: NaN -- the rays that miss the
-        jet), so the host array is produced by two engines at once: host threads write the
-        constants of the first `a` planes with streaming stores and drop in the packed columns
-        of the jet-crossing rays (rjp_pack_rays -> pinned copy -> rjp_host_assemble), while the
-        copy engine moves the other planes as they are.  `a` follows the measured rates of the
-        two, so that both finish together; the result is bit-identical to the plain copy."""
+        jet), so only the packed columns of the jet-crossing rays cross PCIe (`_stage_columns`)
+        and host threads produce the array: constants with streaming stores, columns dropped in
+        (rjp_host_assemble; measured 135-170 GB/s with 16 threads against 57 GB/s for the plain
+        copy of the dense cube, tools/e2e_probe.py).  `sibling`: the other cube of the same line
+        pass; its columns are staged meanwhile, so that handing it over next starts at once.
+        RAJEPY_B200_HOST_SPLIT < 1 leaves that fraction of the planes to the copy engine instead
+        (no gain on the boxes measured: the two engines share the host memory bandwidth).
+        The result is bit-identical to the plain copy."""
         torch = _torch()
         lib = _cabi.load()
         d = self._dev
@@ -1231,60 +1267,39 @@ class JetModel:
         nch, plane = cube.shape
         if nch == 0:
             return
-        frac = os.environ.get("RAJEPY_B200_HOST_SPLIT")
         n = self._n_active()
+        split = float(os.environ.get("RAJEPY_B200_HOST_SPLIT", "1.0"))
         if plane % 2 or n == 0 or n > 0.3 * plane:   # (a jet that covers the sky: nothing to gain)
             split = 0.0
-        elif frac is not None:
-            split = max(0.0, min(1.0, float(frac)))
-        elif _HANDOVER["cpu_gbs"] and _HANDOVER["dma_gbs"]:
-            split = _HANDOVER["cpu_gbs"] / (_HANDOVER["cpu_gbs"] + _HANDOVER["dma_gbs"])
-        else:
-            split = 0.5
-        a = max(0, min(nch, int(round(nch * split))))
+        a = max(0, min(nch, int(round(nch * max(0.0, min(1.0, split))))))
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
-            ev_cols = torch.cuda.Event()
+            cols_h = ev = None
             if a > 0:
-                if d.get("rays_host") is None:
-                    ids_h = torch.empty(n, dtype=torch.int32, pin_memory=True)
-                    ids_h.copy_(d["rays"][:n], non_blocking=True)
-                    d["rays_host"] = ids_h
-                cols = torch.empty((a, n), dtype=torch.float64, device=dev)
-                _cabi.check(lib.rjp_pack_rays(cube.data_ptr(), plane, d["rays"].data_ptr(), n, n,
-                                              a, cols.data_ptr(), stream.cuda_stream),
-                            "rjp_pack_rays")
-                _launched()
-                cols_h = torch.empty((a, n), dtype=torch.float64, pin_memory=True)
-                cols_h.copy_(cols, non_blocking=True)
-            ev_cols.record(stream)
+                cols_h, ev = self._stage_columns(cube)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             if a < nch:
                 out[a:].copy_(cube[a:], non_blocking=True)
             e1.record(stream)
-            t_cpu = 0.0
+            if a > 0 and sibling is not None and sibling.shape == cube.shape:
+                self._stage_columns(sibling)
             if a > 0:
-                ev_cols.synchronize()
+                ev.synchronize()
                 t0 = _time.perf_counter()
                 st = lib.rjp_host_assemble(out.data_ptr(), a, plane, d["rays_host"].data_ptr(), n,
                                            cols_h.data_ptr(), n, float(fill), _host_threads())
                 _cabi.check(st, "rjp_host_assemble")
                 t_cpu = _time.perf_counter() - t0
-            stream.synchronize()
-            # rates for the next split (both engines were running at the same time)
-            if a > 0 and t_cpu > 0:
-                r = a * plane * 8 / t_cpu / 1e9
-                _HANDOVER["cpu_gbs"] = r if not _HANDOVER["cpu_gbs"] else \
-                    0.5 * (r + _HANDOVER["cpu_gbs"])
+                if t_cpu > 0:
+                    _HANDOVER["cpu_gbs"] = a * plane * 8 / t_cpu / 1e9
             if a < nch:
+                stream.synchronize()
                 ms = e0.elapsed_time(e1)
                 if ms > 0:
-                    r = (nch - a) * plane * 8 / (ms * 1e-3) / 1e9
-                    _HANDOVER["dma_gbs"] = r if not _HANDOVER["dma_gbs"] else \
-                        0.5 * (r + _HANDOVER["dma_gbs"])
+                    _HANDOVER["dma_gbs"] = (nch - a) * plane * 8 / (ms * 1e-3) / 1e9
 
-    def _shared_cube(self, cube, fill, nch):
+    def _shared_cube(self, cube, fill, nch, sibling=None):
         """Channel-sharded hand-over: (nch, nx, nz) float64 in POSIX shared memory, every rank
         writing the planes it integrated (collective over the default process group).  The
         host ranks get the array, the others None."""
@@ -1297,7 +1312,8 @@ class JetModel:
         seg = hostshare.segment(nch * plane * 8, self._chan_rank)
         mine = seg.tensor(c_lo * plane * 8, (c_hi - c_lo, plane))     # page-locked view
         if c_hi > c_lo:
-            self._handover(cube.view(c_hi - c_lo, plane), fill, mine)
+            self._handover(cube.view(c_hi - c_lo, plane), fill, mine,
+                           None if sibling is None else sibling.view(c_hi - c_lo, plane))
         dist.barrier()
         wanted = self._host_ranks is None or self._chan_rank in self._host_ranks
         if not wanted:
@@ -1394,7 +1410,7 @@ class JetModel:
             out["flux_ff"] = conv(self._continuum_images_device(cont_freqs, 'flux'), lead=nf)
         if line is not None:
             if host:
-                out["tau_rrl"] = self._host_cube(res["tau"], 0.0, nch)
+                out["tau_rrl"] = self._host_cube(res["tau"], 0.0, nch, sibling=res["flux"])
                 out["flux_rrl"] = self._host_cube(res["flux"], float("nan"), nch)
             else:
                 out["tau_rrl"] = conv(res["tau"], lead=nch)
@@ -1548,7 +1564,7 @@ class JetModel:
             return tau[0] if scalar else tau
         res = self._pass(rrl, freqs, contsub=self._line_contsub_hint(), want_tau=True,
                          want_flux=True)
-        tau = self._host_cube(res["tau"], 0.0, freqs.size)
+        tau = self._host_cube(res["tau"], 0.0, freqs.size, sibling=res["flux"])
         if tau is None:
             return None
         if scalar:
