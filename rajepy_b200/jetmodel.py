@@ -1412,6 +1412,10 @@ class JetModel:
             if host:
                 out["tau_rrl"] = self._host_cube(res["tau"], 0.0, nch, sibling=res["flux"])
                 out["flux_rrl"] = self._host_cube(res["flux"], float("nan"), nch)
+            elif self._chan_world > 1:
+                # channel-sharded: the planes [c_lo, c_hi) this rank integrated stay with it
+                out["tau_rrl"], out["flux_rrl"] = res["tau"], res["flux"]
+                out["channels"] = (res["c_lo"], res["c_hi"])
             else:
                 out["tau_rrl"] = conv(res["tau"], lead=nch)
                 out["flux_rrl"] = conv(res["flux"], lead=nch)
