@@ -448,7 +448,7 @@ def run_gpu(args):
             img_bit = bool(torch.equal(torch.nan_to_num(s_ff), torch.nan_to_num(rs_ff)))
             img_rel = max_rel(s_ff.cpu().numpy(), rs_ff.cpu().numpy())
             shard_check = {"sharded_equals_single": bool(rel <= 1e-6 and tot_rel <= 1e-9
-                                                         and img_rel <= 1e-12),
+                                                         and img_rel <= 1e-9),
                            "bit_identical_cubes": bit, "cube_max_rel_diff": rel,
                            "channel_totals_max_rel_diff": tot_rel,
                            "continuum_images_bit_identical": img_bit,
@@ -456,7 +456,7 @@ def run_gpu(args):
                            "what": "rank 0's cube planes (tau_rrl, flux_rrl) and the "
                                    "all-gathered per-channel flux totals of ALL ranks against "
                                    "an unsharded model on rank 0's GPU (bars: 1e-6 on the "
-                                   "cubes like the parity bar, 1e-9 on the totals, 1e-12 on "
+                                   "cubes like the parity bar, 1e-9 on the totals and on "
                                    "the continuum images).  x-slabs run the same kernels on "
                                    "the same rays: bit-identical.  Channel blocks use another "
                                    "thread layout than the 512-channel kernel: the cells of a "

@@ -232,6 +232,10 @@ int64_t rjp_ray_list_chunks(int64_t nray);
  *   ray i of the slab is element cube_offset + i of every plane of cube_plane elements, so
  *   a slab can write straight into its rows of a full-size [nchan][nx*nz] cube
  *   (cube_plane = nx*nz, cube_offset = x_lo*nz).
+ *   travel_cells / vlos_cells: optional (NULL) user-assigned per-cell grids [slab cells] double
+ *   -- the `ts` and `vel` setters of the reference (classes.py:857-859, :1097-1099): travel time
+ *   from the jet base [s] (NaN: the cell's density is dropped like the reference's nansum does)
+ *   and line-of-sight velocity incl. v_lsr [km/s]; NULL = recomputed from the cell indices.
  * On return all work is ordered on `stream` (stream2 is joined back).              */
 int rjp_integrate(const rjp_model* m_host, const rjp_epoch* ep_host,
                   const rjp_continuum* cont_host, const rjp_cell* cells,
@@ -239,7 +243,8 @@ int rjp_integrate(const rjp_model* m_host, const rjp_epoch* ep_host,
                   int32_t n_active_hint, double* em, double* kff, double* tsum,
                   int32_t* tcount, const rjp_line* line_host, const rjp_channels* ch_host,
                   int32_t nchan, int32_t contsub, double* tau_rrl, double* flux_rrl,
-                  int64_t cube_plane, int64_t cube_offset, void* stream, void* stream2);
+                  int64_t cube_plane, int64_t cube_offset, const double* travel_cells,
+                  const double* vlos_cells, void* stream, void* stream2);
 
 /* Sparse exchange of cube tiles between x-slabs (multi-GPU): 94 % of the rays
  * of the BASELINE jet miss the jet and carry constants (tau_L = 0, flux = NaN) that every rank

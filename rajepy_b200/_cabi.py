@@ -125,7 +125,8 @@ def load():
     lib.rjp_ray_list_chunks.restype = i64
     lib.rjp_integrate.argtypes = [C.POINTER(Model), C.POINTER(Epoch), C.POINTER(Continuum),
                                   vp, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(Line),
-                                  C.POINTER(Channels), i32, i32, vp, vp, i64, i64, vp, vp]
+                                  C.POINTER(Channels), i32, i32, vp, vp, i64, i64, vp, vp, vp,
+                                  vp]
     lib.rjp_pack_rays.argtypes = [vp, i64, vp, i32, i32, i32, vp, vp]
     lib.rjp_scatter_rays.argtypes = [vp, i32, vp, i32, i32, vp, i64, vp]
     lib.rjp_fill_missed.argtypes = [vp, i64, i32, i64, i64, i64, i64, vp, vp, i32, vp]

@@ -17,7 +17,7 @@ int rjp_launch_integrate(const rjp_model*, const rjp_epoch*, const rjp_continuum
                          const rjp_cell*, const int32_t*, const int32_t*, const int32_t*,
                          int, double*, double*, double*, int32_t*, const rjp_line*,
                          const rjp_channels*, int, int, double, double*, double*, long long,
-                         long long, cudaStream_t, cudaStream_t);
+                         long long, const double*, const double*, cudaStream_t, cudaStream_t);
 int rjp_launch_fill_missed(const int32_t*, long long, int, long long, long long, long long,
                            long long, double*, double*, int, cudaStream_t);
 int rjp_launch_pack_rays(const double*, long long, const int32_t*, int, int, int, double*,
@@ -139,7 +139,8 @@ extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_
                              double* kff, double* tsum, int32_t* tcount, const rjp_line* ln,
                              const rjp_channels* ch, int32_t nchan, int32_t contsub,
                              double* tau_rrl, double* flux_rrl, int64_t cube_plane,
-                             int64_t cube_offset, void* stream, void* stream2) {
+                             int64_t cube_offset, const double* travel_cells,
+                             const double* vlos_cells, void* stream, void* stream2) {
   if (!model_ok(m) || !ep || !ct || !cells || !em || !kff || !tsum || !tcount || nchan < 0)
     return RJP_ERR_ARG;
   if (ep->n_blue < 0 || ep->n_blue > RJP_MAX_BURSTS || ep->n_red < 0 ||
@@ -157,6 +158,7 @@ extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_
                                            em, kff, tsum, tcount,
                                            ln, ch, nchan, contsub, ln ? ln->dn_max : 0.0,
                                            tau_rrl, flux_rrl, cube_plane, cube_offset,
+                                           travel_cells, vlos_cells,
                                            (cudaStream_t)stream, (cudaStream_t)stream2));
 }
 

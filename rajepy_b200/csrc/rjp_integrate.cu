@@ -89,15 +89,25 @@ __device__ __forceinline__ bool empty_cell(const double2& c) {
 // (non-inlined) functions that take pointers, so each CTA stages the parameter blocks
 // in shared memory once (1.2 KB) instead of every thread copying them to its
 // local-memory stack.  Two derived travel-time constants are added on the way.
+// User-assigned per-cell grids (the `ts` / `vel` setters of the reference, classes.py:857-859,
+// :1097-1099): when given, the travel time [s] / line-of-sight velocity [km/s] of a cell is
+// read from the slab-shaped array instead of being recomputed from the cell indices.
+struct CellGrids {
+  const double* travel;
+  const double* vlos;
+};
+
 struct Params {
   rjp_model m;
   rjp_epoch ep;
+  CellGrids ov;
   double tt_cst;   // MR0^q_v / (V0 (1 - q_v + eps q^d_v))          (geometry.py:154)
   double tt_f0;    // tt_cst * MR0^(1 - q_v): indefinite integral at r_0 when q^d_v = 0
 };
 
 __device__ __forceinline__ void stage_params(Params* s_p, const rjp_model& m,
-                                             const rjp_epoch& ep) {
+                                             const rjp_epoch& ep,
+                                             const CellGrids ov = CellGrids{nullptr, nullptr}) {
   const int nm = sizeof(rjp_model) / 4, ne = sizeof(rjp_epoch) / 4;
   const uint32_t* gm = reinterpret_cast<const uint32_t*>(&m);
   const uint32_t* ge = reinterpret_cast<const uint32_t*>(&ep);
@@ -106,6 +116,7 @@ __device__ __forceinline__ void stage_params(Params* s_p, const rjp_model& m,
   for (int i = threadIdx.x; i < nm; i += blockDim.x) dm[i] = gm[i];
   for (int i = threadIdx.x; i < ne; i += blockDim.x) de[i] = ge[i];
   if (threadIdx.x == 0) {
+    s_p->ov = ov;
     const double MR0 = m.mr0 * m.au_m, V0 = m.v0 * 1e3;
     const double cst = powq(MR0, m.q_v) / (V0 * (1.0 - m.q_v + m.eps * m.qd_v));
     s_p->tt_cst = cst;
@@ -160,7 +171,9 @@ __device__ __forceinline__ Decoded decode(const double2& c, const Params& P, con
     const double y = __dadd_rn(corner(m.cs, iy, m.ny), m.cs / 2.0);
     const double r = __dadd_rn(__dmul_rn(m.sa, y), __dmul_rn(m.ca, ray.z1));
     double travel;
-    if (m.qd_v == 0.0) {
+    if (P.ov.travel != nullptr) {
+      travel = P.ov.travel[((size_t)(ix - m.x_lo) * m.ny + iy) * m.nz + iz];
+    } else if (m.qd_v == 0.0) {
       const double rad = (r_shifted(m, fabs(r)) + m.mr0 - m.r0) * m.au_m;
       const double e = 1.0 - m.q_v;
       travel = P.tt_cst * ((e == 1.0) ? rad : pow_call(rad, e)) - P.tt_f0;
@@ -234,13 +247,14 @@ __device__ __forceinline__ void reduce_and_store(ContAcc a, const rjp_continuum&
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB)
 integrate_continuum_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
+                           const CellGrids ov,
                            const double2* __restrict__ cells, double* __restrict__ em,
                            double* __restrict__ kff, double* __restrict__ tsum,
                            int32_t* __restrict__ tcount) {
   __shared__ double s_red[3 * 8 * ZT];
   __shared__ int s_cnt[8 * ZT];
   __shared__ Params s_p;
-  stage_params(&s_p, m, ep);
+  stage_params(&s_p, m, ep, ov);
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int ztiles = (m.nz + ZT - 1) / ZT;
   const int xl = blockIdx.x / ztiles;
@@ -270,9 +284,11 @@ integrate_continuum_kernel(const rjp_model m, const rjp_epoch ep, const rjp_cont
 // ------------------------------------------------------------------ line channels (K4)
 __device__ __noinline__ LineEntry make_entry(const Decoded& d, const rjp_model& m,
                                              const rjp_line& ln, double dn_max, int ix,
-                                             int iy, int iz) {
+                                             int iy, int iz, const double* vlos_grid) {
   LineEntry e;
-  const double vlos = velocity_of(m, centroid_rw(m, ix, iy, iz)).vlos_rel + m.v_lsr;
+  const double vlos = vlos_grid
+      ? vlos_grid[((size_t)(ix - m.x_lo) * m.ny + iy) * m.nz + iz]
+      : velocity_of(m, centroid_rw(m, ix, iy, iz)).vlos_rel + m.v_lsr;
   const double shift = -ln.nu0 * (vlos * ln.dopp);           // nu0_cell - nu0 (physics.py:558)
   const double nu0c = ln.nu0 + shift;
   // functions of the temperature alone: precomputed on the host for the temperature most
@@ -520,13 +536,14 @@ __global__ void scatter_rays_kernel(const double* __restrict__ in, int n_stride,
 // over the list.
 __global__ void __launch_bounds__(256)
 continuum_rays_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
+                      const CellGrids ov,
                       const double2* __restrict__ cells, const int2* __restrict__ extents,
                       const int32_t* __restrict__ ray_list,
                       const int32_t* __restrict__ n_active_dev,
                       double* __restrict__ em, double* __restrict__ kff,
                       double* __restrict__ tsum, int32_t* __restrict__ tcount) {
   __shared__ Params s_p;
-  stage_params(&s_p, m, ep);
+  stage_params(&s_p, m, ep, ov);
   const int lane = threadIdx.x & 31;
   const int n_active = *n_active_dev;
   const int nw = gridDim.x * (blockDim.x >> 5);
@@ -706,6 +723,7 @@ __global__ void __maxnreg__(RJP_LINE_MAXNREG)
 __global__ void __launch_bounds__(MAXT, MINB)
 #endif
 integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
+                      const CellGrids ov,
                       const rjp_line ln, const rjp_channels ch, const int nchan,
                       const int c_first, const int contsub, const double dn_max,
                       const double2* __restrict__ cells, const int2* __restrict__ extents,
@@ -726,7 +744,7 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   __shared__ int s_woff[2][MAXT / 32 + 1];
   static_assert(sizeof(LineEntry) == sizeof(FastEntry), "shared batch buffer");
   RJP_STAMP_BEGIN(0)
-  stage_params(&s_p, m, ep);
+  stage_params(&s_p, m, ep, ov);
   if (threadIdx.x == 0) s_ln = ln;
   for (int i = threadIdx.x; i < VT_TAB_F4; i += blockDim.x)
     s_tab[i] = reinterpret_cast<const float4*>(g_vt_core)[i];
@@ -788,7 +806,8 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
       if (!empty_cell(c)) {
         const Decoded d = decode(c, s_p, rc, ix, iy, iz);
         accumulate(ca, d, ct.t_exponent);
-        if (d.ne_ok && d.t_ok) e = make_entry(d, s_p.m, s_ln, dn_max, ix, iy, iz);
+        if (d.ne_ok && d.t_ok)
+          e = make_entry(d, s_p.m, s_ln, dn_max, ix, iy, iz, s_p.ov.vlos);
       }
     }
     const bool fast = fast_class(e);
@@ -1137,8 +1156,10 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
                                     const rjp_line* ln, const rjp_channels* ch, int nchan,
                                     int contsub, double dn_max, double* tau_rrl,
                                     double* flux_rrl, long long cube_plane,
-                                    long long cube_offset, cudaStream_t stream,
+                                    long long cube_offset, const double* travel_cells,
+                                    const double* vlos_cells, cudaStream_t stream,
                                     cudaStream_t stream2) {
+  const CellGrids ov = {travel_cells, vlos_cells};
   const int nxs = m->x_hi - m->x_lo;
   const long long ctas = (long long)nxs * ((m->nz + ZT - 1) / ZT);
   if (ctas <= 0 || ctas > 2147483647LL) return RJP_ERR_ARG;
@@ -1149,8 +1170,8 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
     // no extents: dense sweep over the whole state (continuum only; the API demands extents
     // for line passes)
     if (lines) return RJP_ERR_ARG;
-    integrate_continuum_kernel<2><<<(unsigned)ctas, 256, 0, stream>>>(*m, *ep, *ct, c4, em, kff,
-                                                                     tsum, tcount);
+    integrate_continuum_kernel<2><<<(unsigned)ctas, 256, 0, stream>>>(*m, *ep, *ct, ov, c4, em,
+                                                                     kff, tsum, tcount);
     return RJP_OK;
   }
   const size_t nray = (size_t)nxs * m->nz;
@@ -1219,7 +1240,7 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
                               : (size_t)sms * (B) * (size_t)env_int("RJP_GRID_FACTOR", 16);   \
     if (grid_ > nray) grid_ = nray;                                                           \
     integrate_line_kernel<T, B, U, G><<<(unsigned)grid_, threads, 0, ls>>>(                   \
-        *m, *ep, *ct, *ln, cb, nc, c0, contsub, dn_max, c4, ex2, ray_list, n_active, em_o,    \
+        *m, *ep, *ct, ov, *ln, cb, nc, c0, contsub, dn_max, c4, ex2, ray_list, n_active, em_o, \
         kff, tsum, tcount, t_out, f_out, plane, coff);                                        \
   } while (0)
       if (threads <= 32 && uni) {
@@ -1241,7 +1262,7 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
   } else {
     size_t grid = (nray + 7) / 8;
     if (grid > (size_t)sms * 8) grid = (size_t)sms * 8;
-    continuum_rays_kernel<<<(unsigned)grid, 256, 0, ls>>>(*m, *ep, *ct, c4, ex2, ray_list,
+    continuum_rays_kernel<<<(unsigned)grid, 256, 0, ls>>>(*m, *ep, *ct, ov, c4, ex2, ray_list,
                                                           n_active, em, kff, tsum, tcount);
   }
   if (fork) {

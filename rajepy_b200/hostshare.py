@@ -31,25 +31,31 @@ class Segment:
             except Exception:  # noqa: BLE001
                 pass
         self.busy = False
-        self.registered = False
+        self.registered = {}          # (offset, nbytes) page-locked by THIS process
         self._np = np.ndarray((nbytes,), dtype=np.uint8, buffer=self.shm.buf)
 
-    def _register(self):
-        if self.registered:
+    def _register(self, offset, nbytes):
+        """Page-lock [offset, offset + nbytes) for this process's GPU (only the planes the rank
+        writes: the pinned total over all ranks stays one cube, whatever their number)."""
+        if nbytes == 0 or (offset, nbytes) in self.registered:
             return
         import torch
-        err = torch.cuda.cudart().cudaHostRegister(self._np.ctypes.data, self.nbytes, 0)
+        page = 4096
+        lo = offset // page * page
+        hi = -(-(offset + nbytes) // page) * page
+        hi = min(hi, -(-self.nbytes // page) * page)
+        err = torch.cuda.cudart().cudaHostRegister(self._np.ctypes.data + lo, hi - lo, 0)
         code = getattr(err, "value", err)
         code = code[0] if isinstance(code, tuple) else code
         if int(code) != 0:
-            raise RuntimeError(f"cudaHostRegister of {self.nbytes} bytes failed ({err})")
-        self.registered = True
+            raise RuntimeError(f"cudaHostRegister of {hi - lo} bytes failed ({err})")
+        self.registered[(offset, nbytes)] = lo
 
     def tensor(self, offset, shape):
-        """float64 torch view of `shape` at byte `offset` (the whole segment is page-locked)."""
+        """float64 torch view of `shape` at byte `offset`, page-locked."""
         import torch
-        self._register()
         n = int(np.prod(shape))
+        self._register(offset, 8 * n)
         view = self._np[offset: offset + 8 * n].view(np.float64).reshape(shape)
         return torch.from_numpy(view)
 
@@ -65,9 +71,9 @@ class Segment:
 
     def close(self):
         try:
-            if self.registered:
-                import torch
-                torch.cuda.cudart().cudaHostUnregister(self._np.ctypes.data)
+            import torch
+            for lo in self.registered.values():
+                torch.cuda.cudart().cudaHostUnregister(self._np.ctypes.data + lo)
         except Exception:  # noqa: BLE001
             pass
         self._np = None

@@ -623,9 +623,6 @@ class JetModel:
         return self._dev
 
     def _launch_fill(self, tie_cap=_TIE_CAPACITY):
-        if 'travel' in self._overrides or 'vel' in self._overrides:
-            raise NotImplementedError("user-assigned `ts` / `vel` grids are not supported by the "
-                                      "CUDA path (`ion_fraction` and `temperature` are)")
         torch = _torch()
         lib = _cabi.load()
         dev = self._device()
@@ -681,6 +678,22 @@ class JetModel:
                                             self._stream())
                 _cabi.check(st, "rjp_override_cells")
                 _launched()
+        # user-assigned travel-time / velocity grids (the `ts` / `vel` setters): the integrators
+        # read them per cell instead of recomputing the analytic laws
+        d["travel_grid"] = d["vlos_grid"] = None
+        shape = (self._x_hi - self._x_lo, self._ny, self._nz)
+        if 'travel' in self._overrides:
+            arr = np.ascontiguousarray(np.asarray(self._overrides['travel'], dtype=np.float64)
+                                       [self._x_lo:self._x_hi])
+            if arr.shape != shape:
+                raise ValueError(f"assigned ts grid has shape {arr.shape}")
+            d["travel_grid"] = torch.from_numpy(arr).to(dev)
+        if 'vel' in self._overrides:
+            arr = np.ascontiguousarray(np.asarray(self._overrides['vel'][1], dtype=np.float64)
+                                       [self._x_lo:self._x_hi])
+            if arr.shape != shape:
+                raise ValueError(f"assigned v_los grid has shape {arr.shape}")
+            d["vlos_grid"] = torch.from_numpy(arr).to(dev)
 
     def _validate_fill(self):
         """Wait for the fill's tie report (not for anything queued behind it), let the host
@@ -938,6 +951,12 @@ class JetModel:
     @property
     def chi_xyz(self):
         """Burst factor per cell (classes.py:861-870)"""
+        if 'travel' in self._overrides:
+            # user-assigned launch times: the reference's own expression on the host
+            ts = self.ts
+            with np.errstate(all='ignore'):
+                return np.where(self.rr < 0, self._jml_t_rj(ts) / self._ss_jml_rj,
+                                self._jml_t_bj(ts) / self._ss_jml_bj)
         return self._field('chi', cache=False)
 
     @property
@@ -1065,7 +1084,8 @@ class JetModel:
                                        d["n_active_dev"].data_ptr(), 0,
                                        em.data_ptr(), kff.data_ptr(),
                                        tsum.data_ptr(), cnt.data_ptr(), None, None, 0, 1,
-                                       None, None, 0, 0, self._stream(), None)
+                                       None, None, 0, 0, *self._cell_grid_ptrs(),
+                                       self._stream(), None)
             else:
                 c_lo, c_hi = 0, len(freqs)
                 dn_all = None
@@ -1096,7 +1116,7 @@ class JetModel:
                                        nch, 1 if contsub else 0,
                                        tau.data_ptr() if (want_tau and lines) else None,
                                        flux.data_ptr() if (want_flux and lines) else None,
-                                       plane, coff,
+                                       plane, coff, *self._cell_grid_ptrs(),
                                        self._stream(), d["stream2"].cuda_stream)
                 if self._world > 1:
                     _cabi.check(st, "rjp_integrate")
@@ -1112,6 +1132,11 @@ class JetModel:
             # the state has been patched, integrate again
             return self._pass(line, freqs, contsub, want_tau, want_flux)
         return self._cont if line is None else self._line
+
+    def _cell_grid_ptrs(self):
+        d = self._dev
+        return tuple(None if d.get(k) is None else d[k].data_ptr()
+                     for k in ("travel_grid", "vlos_grid"))
 
     def _line_structs(self, line, freqs, dev, dn_max=None):
         """Host scalars of the LTE line opacity (classes.py:1159-1169; rrls.py) and the

@@ -136,6 +136,42 @@ def test_user_assigned_temperature_and_ion_fraction():
     assert_parity(jm.optical_depth_rrl('H58a', chans), oj.optical_depth_rrl('H58a', chans),
                   "tau_rrl", floor=1e-290)
     assert np.array_equal(np.nan_to_num(jm.temperature), np.nan_to_num(0.5 * t3d))
-    with pytest.raises(NotImplementedError):
-        jm.vel = jm.vel
-        jm.emission_measure()
+
+
+def test_user_assigned_launch_times_and_velocities():
+    """The `ts` / `vel` setters (classes.py:857-859, :1097-1099): the integrators then read the
+    travel time / line-of-sight velocity of every cell from the assigned grids."""
+    import copy
+    import rajepy_b200 as rb
+    from oracle import rajepy_oracle as orc
+    log = rb.logger.Log(os.path.join(tempfile.mkdtemp(), "m.log"), verbose=False)
+    p = cases.case_inclined()
+    jm = rb.JetModel(copy.deepcopy(p), log=log)
+    oj = orc.OracleJet(copy.deepcopy(p))
+    jm.time = oj.time = 1.1 * con.year
+    base = (jm.emission_measure(), jm.flux_ff(5e9))
+    # slower material (travel times stretched) and a sheared velocity field
+    travel = oj.travel_time() * 1.7 + 3e5
+    vx, vlos, vz = oj.vel()
+    shear = 4.0 * np.sin(np.arange(vlos.shape[1]) / 5.0)[None, :, None]
+    new_v = (vx, vlos + shear, vz)
+    jm.ts = travel              # the reference's setter takes the travel-time grid
+    jm.vel = new_v
+    oj._c["tt"] = travel
+    oj._c["vel"] = new_v
+    assert np.array_equal(np.nan_to_num(jm.ts), np.nan_to_num(jm.time - travel))
+    assert jm.vel is new_v
+    assert_parity(jm.chi_xyz, oj.chi_xyz(), "chi", rtol=1e-12)
+    em = jm.emission_measure()
+    assert_parity(em, oj.emission_measure(), "EM")
+    assert not np.array_equal(em, base[0])          # the bursts sit elsewhere now
+    f = np.array([5e9, 4.3e10])
+    assert_parity(jm.optical_depth_ff(f), oj.optical_depth_ff(f), "tau_ff")
+    assert_parity(jm.flux_ff(f), oj.flux_ff(f), "S_ff", floor=cancellation_floor_ff(oj, f))
+    chans = cases.line_channels(orc.rrl_nu_0('H', 58, 1), 12, 5e5)
+    assert_parity(jm.optical_depth_rrl('H58a', chans), oj.optical_depth_rrl('H58a', chans),
+                  "tau_rrl", floor=1e-290)
+    fl = np.nan_to_num(cancellation_floor_line(oj, chans) + cancellation_floor_ff(oj, chans))
+    assert_parity(jm.flux_rrl('H58a', chans, contsub=False),
+                  oj.flux_rrl('H58a', chans, contsub=False), "S_rrl", floor=fl)
+    jm.release()

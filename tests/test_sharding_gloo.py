@@ -198,7 +198,7 @@ def _chan_worker(rank, world, port, nchan, out_dir):
     ok = np.array_equal(tot.numpy(), np.nansum(cube, axis=1))
     for _ in range(2):                       # second round reuses the pooled segment
         seg = hostshare.segment(nchan * plane * 8, rank)
-        seg._register = lambda: None         # no CUDA here
+        seg._register = lambda off, nb: None  # no CUDA here
         mine = seg.tensor(lo * plane * 8, (hi - lo, plane))
         mine.copy_(local)
         dist.barrier()
