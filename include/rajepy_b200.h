@@ -236,7 +236,14 @@ int64_t rjp_ray_list_chunks(int64_t nray);
  *   -- the `ts` and `vel` setters of the reference (classes.py:857-859, :1097-1099): travel time
  *   from the jet base [s] (NaN: the cell's density is dropped like the reference's nansum does)
  *   and line-of-sight velocity incl. v_lsr [km/s]; NULL = recomputed from the cell indices.
+ *   line_scratch / line_max_cells (line passes only): DEVICE scratch of
+ *   rjp_line_scratch_bytes(m, line_max_cells) bytes, where line_max_cells >= the summed
+ *   lengths of the extents of the listed rays (the prepared cells of every jet-crossing ray
+ *   are staged there between the two kernels of a line pass: ray_prepare_kernel evaluates the
+ *   per-cell line constants once, integrate_line_kernel is the channel loop alone).  A ray
+ *   whose cells do not fit gets NaN in every channel of both cubes.
  * On return all work is ordered on `stream` (stream2 is joined back).              */
+int64_t rjp_line_scratch_bytes(const rjp_model* m_host, int64_t line_max_cells);
 int rjp_integrate(const rjp_model* m_host, const rjp_epoch* ep_host,
                   const rjp_continuum* cont_host, const rjp_cell* cells,
                   const int32_t* extents, const int32_t* ray_list, const int32_t* n_active,
@@ -244,7 +251,8 @@ int rjp_integrate(const rjp_model* m_host, const rjp_epoch* ep_host,
                   int32_t* tcount, const rjp_line* line_host, const rjp_channels* ch_host,
                   int32_t nchan, int32_t contsub, double* tau_rrl, double* flux_rrl,
                   int64_t cube_plane, int64_t cube_offset, const double* travel_cells,
-                  const double* vlos_cells, void* stream, void* stream2);
+                  const double* vlos_cells, void* line_scratch, int64_t line_max_cells,
+                  void* stream, void* stream2);
 
 /* Sparse exchange of cube tiles between x-slabs (multi-GPU): 94 % of the rays
  * of the BASELINE jet miss the jet and carry constants (tau_L = 0, flux = NaN) that every rank

@@ -66,7 +66,7 @@ EXPORTS = ("rjp_strerror", "rjp_last_cuda_error", "rjp_abi_version", "rjp_struct
            "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field", "rjp_ray_list", "rjp_integrate",
            "rjp_continuum_images", "rjp_voigt_profile", "rjp_brick_count", "rjp_pack_rays",
            "rjp_scatter_rays", "rjp_fill_missed", "rjp_los_means", "rjp_override_cells",
-           "rjp_ray_list_chunks", "rjp_host_assemble")
+           "rjp_ray_list_chunks", "rjp_host_assemble", "rjp_line_scratch_bytes")
 
 ABI_VERSION = 5      # RJP_ABI_VERSION of include/rajepy_b200.h this binding was written for
 
@@ -126,7 +126,9 @@ def load():
     lib.rjp_integrate.argtypes = [C.POINTER(Model), C.POINTER(Epoch), C.POINTER(Continuum),
                                   vp, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(Line),
                                   C.POINTER(Channels), i32, i32, vp, vp, i64, i64, vp, vp, vp,
-                                  vp]
+                                  i64, vp, vp]
+    lib.rjp_line_scratch_bytes.argtypes = [C.POINTER(Model), i64]
+    lib.rjp_line_scratch_bytes.restype = i64
     lib.rjp_pack_rays.argtypes = [vp, i64, vp, i32, i32, i32, vp, vp]
     lib.rjp_scatter_rays.argtypes = [vp, i32, vp, i32, i32, vp, i64, vp]
     lib.rjp_fill_missed.argtypes = [vp, i64, i32, i64, i64, i64, i64, vp, vp, i32, vp]

@@ -17,7 +17,9 @@ int rjp_launch_integrate(const rjp_model*, const rjp_epoch*, const rjp_continuum
                          const rjp_cell*, const int32_t*, const int32_t*, const int32_t*,
                          int, double*, double*, double*, int32_t*, const rjp_line*,
                          const rjp_channels*, int, int, double, double*, double*, long long,
-                         long long, const double*, const double*, cudaStream_t, cudaStream_t);
+                         long long, const double*, const double*, void*, long long, cudaStream_t,
+                         cudaStream_t);
+long long rjp_launch_line_scratch_bytes(long long, long long);
 int rjp_launch_fill_missed(const int32_t*, long long, int, long long, long long, long long,
                            long long, double*, double*, int, cudaStream_t);
 int rjp_launch_pack_rays(const double*, long long, const int32_t*, int, int, int, double*,
@@ -140,7 +142,8 @@ extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_
                              const rjp_channels* ch, int32_t nchan, int32_t contsub,
                              double* tau_rrl, double* flux_rrl, int64_t cube_plane,
                              int64_t cube_offset, const double* travel_cells,
-                             const double* vlos_cells, void* stream, void* stream2) {
+                             const double* vlos_cells, void* line_scratch,
+                             int64_t line_max_cells, void* stream, void* stream2) {
   if (!model_ok(m) || !ep || !ct || !cells || !em || !kff || !tsum || !tcount || nchan < 0)
     return RJP_ERR_ARG;
   if (ep->n_blue < 0 || ep->n_blue > RJP_MAX_BURSTS || ep->n_red < 0 ||
@@ -152,14 +155,22 @@ extern "C" int rjp_integrate(const rjp_model* m, const rjp_epoch* ep, const rjp_
     if (!tau_rrl && !flux_rrl) return RJP_ERR_ARG;
     if (!extents || !ray_list || !n_active) return RJP_ERR_ARG;
     if (cube_plane < 0 || cube_offset < 0) return RJP_ERR_ARG;
+    if (!line_scratch || line_max_cells < 0) return RJP_ERR_ARG;
   }
   return check_launch(rjp_launch_integrate(m, ep, ct, cells, extents, ray_list, n_active,
                                            n_active_hint,
                                            em, kff, tsum, tcount,
                                            ln, ch, nchan, contsub, ln ? ln->dn_max : 0.0,
                                            tau_rrl, flux_rrl, cube_plane, cube_offset,
-                                           travel_cells, vlos_cells,
+                                           travel_cells, vlos_cells, line_scratch,
+                                           line_max_cells,
                                            (cudaStream_t)stream, (cudaStream_t)stream2));
+}
+
+extern "C" int64_t rjp_line_scratch_bytes(const rjp_model* m, int64_t max_cells) {
+  if (!model_ok(m) || max_cells < 0) return RJP_ERR_ARG;
+  return (int64_t)rjp_launch_line_scratch_bytes((long long)(m->x_hi - m->x_lo) * m->nz,
+                                                (long long)max_cells);
 }
 
 extern "C" int rjp_continuum_images(const double* kff, const double* tsum,

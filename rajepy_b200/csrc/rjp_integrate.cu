@@ -54,7 +54,7 @@ constexpr int RPW = 8;          // rows in flight per warp
 #define RJP_MINB64 8
 #endif
 #ifndef RJP_MINB64U
-#define RJP_MINB64U 8
+#define RJP_MINB64U 12
 #endif
 #ifndef RJP_MINB128
 #define RJP_MINB128 4
@@ -491,7 +491,11 @@ __device__ __forceinline__ void const_drain() {
 
 // The constant writer: every warp of the grid takes work items round-robin (consecutive items
 // go to different CTAs); the warps of a CTA share the two source tiles.
+#ifdef RJP_WRITER_MAXNREG
+__global__ void __maxnreg__(RJP_WRITER_MAXNREG)
+#else
 __global__ void __launch_bounds__(256)
+#endif
 const_tiles_kernel(const ConstJob job) {
   __shared__ __align__(128) double s_zero[CT_SRC];
   __shared__ __align__(128) double s_nan[CT_SRC];
@@ -709,6 +713,162 @@ __device__ __forceinline__ void fast_cells(const FastEntry* __restrict__ s_fast,
   }
 }
 
+// ------------------------------------------------------------------ K4a: prepare the rays
+// What the channel loop needs of a jet-crossing ray, written by ray_prepare_kernel: where its
+// prepared cells sit in the entry buffer (fast-class entries from the front of the ray's
+// segment, the others from its back) and the ray's continuum sums for the flux epilogue.
+struct RayMeta {
+  long long base;     // first entry of the ray's segment
+  int len;            // length of the segment (= length of the ray's extent)
+  int nf, ns;         // fast-class / fp64-class entries
+  int cnt;            // cells with a valid temperature (classes.py:1471-1472)
+  double kray, tsum;  // K (tau_ff = cff * K) and the sum of those temperatures
+};
+static_assert(sizeof(RayMeta) == 40, "RayMeta layout");
+
+// One CTA per jet-crossing ray: every thread prepares one cell of the extent per batch --
+// burst factor, Doppler shift, widths, amplitude, class (decode / make_entry / to_fast: ~1500
+// dependent fp64 instructions per cell, latency-bound) -- and stores the 80-byte entry; the same
+// walk yields the ray's continuum sums (EM, K, sum T, count) and writes its pixels of the four
+// sky images.  This used to be the first phase of every batch INSIDE the channel loop kernel,
+// where its stalled warps took a third of that kernel's warp residency (ncu: 35 % of the stall
+// samples on 16 % of the instructions); as a kernel of its own it is hidden behind thousands of
+// independent rays, and the channel loop kernel is nothing but the channel loop.
+#ifndef RJP_PREP_MINB
+#define RJP_PREP_MINB 16
+#endif
+__global__ void __launch_bounds__(64, RJP_PREP_MINB)
+ray_prepare_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
+                   const CellGrids ov, const rjp_line ln, const double dn_max,
+                   const double2* __restrict__ cells, const int2* __restrict__ extents,
+                   const int32_t* __restrict__ ray_list,
+                   const int32_t* __restrict__ n_active_dev,
+                   unsigned long long* __restrict__ cursor, const long long capacity,
+                   unsigned char* __restrict__ entries, RayMeta* __restrict__ meta,
+                   double* __restrict__ em, double* __restrict__ kff,
+                   double* __restrict__ tsum, int32_t* __restrict__ tcount) {
+  __shared__ Params s_p;
+  __shared__ rjp_line s_ln;
+  __shared__ double s_part[3][2];
+  __shared__ int s_pcnt[2];
+  __shared__ int s_woff[2][3];
+  __shared__ long long s_base;
+  stage_params(&s_p, m, ep, ov);
+  if (threadIdx.x == 0) s_ln = ln;
+  __syncthreads();
+  const int NT = blockDim.x;
+  const int g = threadIdx.x, lane = g & 31, wrp = g >> 5, nwarps = NT >> 5;
+  const int n_active = *n_active_dev;
+  for (int ticket = blockIdx.x; ticket < n_active; ticket += gridDim.x) {
+    const int ray = ray_list[ticket];              // slab-local ray index = xl * nz + iz
+    const int2 ext = extents[ray];
+    const int len = ext.y - ext.x;
+    if (g == 0) {
+      long long b = (long long)atomicAdd(cursor, (unsigned long long)len);
+      if (b + len > capacity) b = -1;              // (cannot happen with an exact capacity)
+      s_base = b;
+    }
+    const int xl = ray / m.nz, iz = ray - xl * m.nz;
+    const int ix = m.x_lo + xl;
+    const Ray rc = ray_of(s_p.m, ix, iz);
+    const double2* col = cells + (size_t)xl * m.ny * m.nz + iz;
+    ContAcc ca = {0.0, 0.0, 0.0, 0};
+    int nf_tot = 0, ns_tot = 0;
+    __syncthreads();
+    const long long base = s_base;
+    for (int y0 = ext.x; y0 < ext.y; y0 += NT) {
+      const int iy = y0 + g;
+      LineEntry e;
+      e.amp = 0.0;
+      if (iy < ext.y) {
+        const double2 c = col[(size_t)iy * m.nz];
+        if (!empty_cell(c)) {
+          const Decoded d = decode(c, s_p, rc, ix, iy, iz);
+          accumulate(ca, d, ct.t_exponent);
+          if (d.ne_ok && d.t_ok)
+            e = make_entry(d, s_p.m, s_ln, dn_max, ix, iy, iz, s_p.ov.vlos);
+        }
+      }
+      // cells that emit no line are dropped; the two classes are compacted in cell order
+      // (deterministic summation order in the channel loop)
+      const bool fast = fast_class(e);
+      const bool slow = e.amp != 0.0 && !fast;
+      const unsigned balf = __ballot_sync(0xffffffffu, fast);
+      const unsigned bals = __ballot_sync(0xffffffffu, slow);
+      if (lane == 0) {
+        s_woff[0][wrp] = __popc(balf);
+        s_woff[1][wrp] = __popc(bals);
+      }
+      __syncthreads();
+      int basef = 0, bases = 0, nf = 0, ns = 0;
+      for (int w = 0; w < nwarps; ++w) {
+        if (w < wrp) {
+          basef += s_woff[0][w];
+          bases += s_woff[1][w];
+        }
+        nf += s_woff[0][w];
+        ns += s_woff[1][w];
+      }
+      const unsigned below = (1u << lane) - 1u;
+      if (base >= 0) {
+        if (fast) {
+          const FastEntry fe = to_fast(e);
+          const long long k = base + nf_tot + basef + __popc(balf & below);
+          reinterpret_cast<FastEntry*>(entries)[k] = fe;
+        }
+        if (slow) {
+          const long long k = base + len - 1 - (ns_tot + bases + __popc(bals & below));
+          reinterpret_cast<LineEntry*>(entries)[k] = e;
+        }
+      }
+      nf_tot += nf;
+      ns_tot += ns;
+      __syncthreads();   // s_woff is rewritten by the next batch
+    }
+    // the ray's continuum sums: warp shuffles, then the warps' partials through shared memory
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ca.kff += __shfl_xor_sync(0xffffffffu, ca.kff, o);
+      ca.tsum += __shfl_xor_sync(0xffffffffu, ca.tsum, o);
+      ca.em += __shfl_xor_sync(0xffffffffu, ca.em, o);
+      ca.cnt += __shfl_xor_sync(0xffffffffu, ca.cnt, o);
+    }
+    if (lane == 0) {
+      s_part[0][wrp] = ca.kff;
+      s_part[1][wrp] = ca.tsum;
+      s_part[2][wrp] = ca.em;
+      s_pcnt[wrp] = ca.cnt;
+    }
+    __syncthreads();
+    if (g == 0) {
+      double kray = 0.0, ts = 0.0, emr = 0.0;
+      int cn = 0;
+      for (int i = 0; i < nwarps; ++i) {
+        kray += s_part[0][i];
+        ts += s_part[1][i];
+        emr += s_part[2][i];
+        cn += s_pcnt[i];
+      }
+      kray *= ct.tau_scale;
+      em[ray] = emr * ct.em_scale;
+      kff[ray] = kray;
+      tsum[ray] = ts;
+      tcount[ray] = cn;
+      RayMeta rm;
+      rm.base = base;
+      rm.len = len;
+      rm.nf = base >= 0 ? nf_tot : 0;
+      rm.ns = base >= 0 ? ns_tot : 0;
+      rm.cnt = base >= 0 ? cn : -1;       // -1: entry buffer too small, the ray's columns = NaN
+      rm.kray = kray;
+      rm.tsum = ts;
+      meta[ticket] = rm;
+    }
+    __syncthreads();   // s_base / s_part are rewritten by the next ray
+  }
+}
+
+// ------------------------------------------------------------------ K4b: the channel loop
 // UNI: the channels are equally spaced (rjp_line.chan_step != 0): the channel offsets are
 // formed on the fly from two per-thread scalars instead of living in 24 registers (16 of
 // which spilled), which is what lets the kernel fit more warps per SM.
@@ -722,37 +882,28 @@ __global__ void __maxnreg__(RJP_LINE_MAXNREG)
 #else
 __global__ void __launch_bounds__(MAXT, MINB)
 #endif
-integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
-                      const CellGrids ov,
-                      const rjp_line ln, const rjp_channels ch, const int nchan,
+integrate_line_kernel(const rjp_line ln, const rjp_channels ch, const int nchan,
                       const int c_first, const int contsub, const double dn_max,
-                      const double2* __restrict__ cells, const int2* __restrict__ extents,
+                      const unsigned char* __restrict__ entries,
+                      const RayMeta* __restrict__ meta,
                       const int32_t* __restrict__ ray_list,
-                      const int32_t* __restrict__ n_active_dev, double* __restrict__ em,
-                      double* __restrict__ kff, double* __restrict__ tsum,
-                      int32_t* __restrict__ tcount, double* __restrict__ tau_rrl,
-                      double* __restrict__ flux_rrl, const size_t plane,
-                      const size_t cube_offset) {
-  __shared__ Params s_p;
-  __shared__ rjp_line s_ln;
-  // one batch of prepared cells: fast-class entries from the front, the others behind them
-  // (both are 80 bytes; +3 zero-amplitude pads for the 4-cell batches of the fp64 path)
+                      const int32_t* __restrict__ n_active_dev,
+                      double* __restrict__ tau_rrl, double* __restrict__ flux_rrl,
+                      const size_t plane, const size_t cube_offset) {
+  // one chunk of prepared cells (80 bytes each; +3 zero-amplitude pads for the 4-cell batches
+  // of the fp64 path)
   __shared__ __align__(16) unsigned char s_raw[(MAXT + 4) * sizeof(LineEntry)];
   __shared__ float4 s_tab[VT_TAB_F4];
-  __shared__ double s_part[3][MAXT / 32];
-  __shared__ int s_pcnt[MAXT / 32];
-  __shared__ int s_woff[2][MAXT / 32 + 1];
   static_assert(sizeof(LineEntry) == sizeof(FastEntry), "shared batch buffer");
+  static_assert(sizeof(LineEntry) == 80, "entries are copied as five 16-byte words");
   RJP_STAMP_BEGIN(0)
-  stage_params(&s_p, m, ep, ov);
-  if (threadIdx.x == 0) s_ln = ln;
   for (int i = threadIdx.x; i < VT_TAB_F4; i += blockDim.x)
     s_tab[i] = reinterpret_cast<const float4*>(g_vt_core)[i];
 
   uint32_t tab = (uint32_t)__cvta_generic_to_shared(s_tab);
   asm volatile("" : "+r"(tab));  // keep it in a register (rematerialising costs S2R + LEA)
   const int NT = blockDim.x;
-  const int g = threadIdx.x, lane = g & 31, wrp = g >> 5, nwarps = NT >> 5;
+  const int g = threadIdx.x;
   const int n_active = *n_active_dev;
 
   // thread g owns channels g, g + NT, g + 2 NT, ...: at every step the lanes of a warp hold
@@ -777,137 +928,85 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   }
 
   __syncthreads();
-  // ray number blockIdx.x, + gridDim.x, ... of the ordered list.  The grid is a fixed multiple
-  // of what fits on the device (the host never knows how many rays cross the jet): CTAs
-  // beyond the list leave at once, a long list gives every CTA a few rays.  Measured on B200:
-  // a grid of exactly-resident CTAs pulling rays from a ticket counter is 7 % SLOWER (5.61 vs
-  // 5.25 ms at 1024^2 rays x 512 channels) -- CTAs of one age advance in lockstep, young CTAs
-  // beside old ones overlap their latency-bound cell preparation with the others' channel loop.
+  // ray number blockIdx.x, + gridDim.x, ... of the ordered list.  The host sizes the grid to
+  // one CTA per ray when it remembers the count of this geometry (rjp_integrate's
+  // n_active_hint), else to a multiple of what fits on the device: CTAs beyond the list leave
+  // at once, a long list gives every CTA a few rays.  Measured on B200: a grid of
+  // exactly-resident CTAs pulling rays from a ticket counter is 7 % SLOWER (5.61 vs 5.25 ms at
+  // 1024^2 rays x 512 channels) -- CTAs of one age advance in lockstep, CTAs of mixed ages
+  // overlap their start-up and epilogue latencies with the others' channel loop.
   for (int ticket = blockIdx.x; ticket < n_active; ticket += gridDim.x) {
+  const RayMeta rm = meta[ticket];
   const int ray = ray_list[ticket];                // slab-local ray index = xl * nz + iz
-  const int2 ext = extents[ray];
-  const int xl = ray / m.nz, iz = ray - xl * m.nz;
-  const int ix = m.x_lo + xl;
   double acc[GCH];
 #pragma unroll
   for (int j = 0; j < GCH; ++j) acc[j] = 0.0;
-  ContAcc ca = {0.0, 0.0, 0.0, 0};
-  const Ray rc = ray_of(s_p.m, ix, iz);
-  const double2* col = cells + (size_t)xl * m.ny * m.nz + iz;
+  const uint4* seg = reinterpret_cast<const uint4*>(entries) + rm.base * 5;
 
-  for (int y0 = ext.x; y0 < ext.y; y0 += NT) {
-    // phase 1: every thread prepares one cell of the extent; cells that emit no line are
-    // dropped and the two classes are compacted in order (deterministic summation order)
-    const int iy = y0 + g;
-    LineEntry e;
-    e.amp = 0.0;
-    if (iy < ext.y) {
-      const double2 c = col[(size_t)iy * m.nz];
-      if (!empty_cell(c)) {
-        const Decoded d = decode(c, s_p, rc, ix, iy, iz);
-        accumulate(ca, d, ct.t_exponent);
-        if (d.ne_ok && d.t_ok)
-          e = make_entry(d, s_p.m, s_ln, dn_max, ix, iy, iz, s_p.ov.vlos);
-      }
-    }
-    const bool fast = fast_class(e);
-    const bool slow = e.amp != 0.0 && !fast;
-    const unsigned balf = __ballot_sync(0xffffffffu, fast);
-    const unsigned bals = __ballot_sync(0xffffffffu, slow);
-    if (lane == 0) {
-      s_woff[0][wrp] = __popc(balf);
-      s_woff[1][wrp] = __popc(bals);
+  // fast class: chunks of NT prepared cells, one 80-byte entry per thread into shared memory,
+  // then every thread adds each of them to its GCH channels
+  for (int c0 = 0; c0 < rm.nf; c0 += NT) {
+    const int cnt = (rm.nf - c0 < NT) ? rm.nf - c0 : NT;
+    if (g < cnt) {
+      const uint4* src = seg + (size_t)(c0 + g) * 5;
+      uint4* dst = reinterpret_cast<uint4*>(s_raw) + g * 5;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) dst[k] = __ldg(src + k);
     }
     __syncthreads();
-    int basef = 0, bases = 0, nf = 0, ns = 0;
-    for (int w = 0; w < nwarps; ++w) {
-      if (w < wrp) {
-        basef += s_woff[0][w];
-        bases += s_woff[1][w];
-      }
-      nf += s_woff[0][w];
-      ns += s_woff[1][w];
-    }
-    FastEntry* s_fast = reinterpret_cast<FastEntry*>(s_raw);
-    LineEntry* s_slow = reinterpret_cast<LineEntry*>(s_raw) + nf;
-    const unsigned below = (1u << lane) - 1u;
-    if (fast) s_fast[basef + __popc(balf & below)] = to_fast(e);
-    if (slow) s_slow[bases + __popc(bals & below)] = e;
+    fast_cells<UNI, GCH>(reinterpret_cast<const FastEntry*>(s_raw), 0, cnt, acc, dn, dnf2,
+                         dstep, dstepf, tab);
     __syncthreads();
-    if (g < 3 && ns > 0) {  // pad the last batch of 4 with zero-amplitude copies
-      LineEntry pad = s_slow[ns - 1];
+  }
+
+  // everything else in fp64 (large or tiny y, steep Planck factor), stored from the back of
+  // the segment: 4 cells at a time, channel loop outermost
+  for (int c0 = 0; c0 < rm.ns; c0 += NT) {
+    const int cnt = (rm.ns - c0 < NT) ? rm.ns - c0 : NT;
+    LineEntry* s_slow = reinterpret_cast<LineEntry*>(s_raw);
+    if (g < cnt) {
+      const uint4* src = seg + (size_t)(rm.len - 1 - (c0 + g)) * 5;
+      uint4* dst = reinterpret_cast<uint4*>(s_raw) + g * 5;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) dst[k] = __ldg(src + k);
+    }
+    __syncthreads();
+    if (g < 3) {  // pad the last batch of 4 with zero-amplitude copies
+      LineEntry pad = s_slow[cnt - 1];
       pad.amp = 0.0;
-      s_slow[ns + g] = pad;
+      s_slow[cnt + g] = pad;
     }
     __syncthreads();
-
-    // phase 2a, fast class: every thread adds each prepared cell to its GCH channels
-    fast_cells<UNI, GCH>(s_fast, 0, nf, acc, dn, dnf2, dstep, dstepf, tab);
-
-    // phase 2b, everything else in fp64 (large or tiny y, steep Planck factor): 4 cells at a
-    // time, channel loop outermost
-    if (ns > 0) {
 #pragma unroll 1
-      for (int j = 0; j < GCH; ++j) {
-        if (g + j * NT >= nchan) break;
-        const double dnj = UNI ? fma((double)j, dstep, dn[0]) : dn[j];
-        double sum = 0.0;
-        for (int i = 0; i < ns; i += 4) {
-          const LineEntry* eb = s_slow + i;
-          double x[4], yy[4], w[4];
-          bool wing = true;
+    for (int j = 0; j < GCH; ++j) {
+      if (g + j * NT >= nchan) break;
+      const double dnj = UNI ? fma((double)j, dstep, dn[0]) : dn[j];
+      double sum = 0.0;
+      for (int i = 0; i < cnt; i += 4) {
+        const LineEntry* eb = s_slow + i;
+        double x[4], yy[4], w[4];
+        bool wing = true;
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            x[v] = fma(dnj, eb[v].inv_s2, eb[v].xs);
-            yy[v] = eb[v].y;
-            wing = wing && (fma(x[v], x[v], yy[v] * yy[v]) >= 36.0);
-          }
-          if (wing) faddeeva_wing_n<4>(x, yy, w);
-          else faddeeva_re_n<4>(x, yy, w);
-#pragma unroll
-          for (int v = 0; v < 4; ++v)
-            sum = fma(eb[v].amp * w[v], planck_factor(eb[v], dnj), sum);
+        for (int v = 0; v < 4; ++v) {
+          x[v] = fma(dnj, eb[v].inv_s2, eb[v].xs);
+          yy[v] = eb[v].y;
+          wing = wing && (fma(x[v], x[v], yy[v] * yy[v]) >= 36.0);
         }
-        acc[j] += sum;
+        if (wing) faddeeva_wing_n<4>(x, yy, w);
+        else faddeeva_re_n<4>(x, yy, w);
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          sum = fma(eb[v].amp * w[v], planck_factor(eb[v], dnj), sum);
       }
+      acc[j] += sum;
     }
     __syncthreads();
-  }
-
-  // the ray's continuum sums (needed by the flux epilogue): warp shuffles, then the warps'
-  // partials through shared memory
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ca.kff += __shfl_xor_sync(0xffffffffu, ca.kff, o);
-    ca.tsum += __shfl_xor_sync(0xffffffffu, ca.tsum, o);
-    ca.em += __shfl_xor_sync(0xffffffffu, ca.em, o);
-    ca.cnt += __shfl_xor_sync(0xffffffffu, ca.cnt, o);
-  }
-  if (lane == 0) {
-    s_part[0][wrp] = ca.kff;
-    s_part[1][wrp] = ca.tsum;
-    s_part[2][wrp] = ca.em;
-    s_pcnt[wrp] = ca.cnt;
-  }
-  __syncthreads();
-  double kray = 0.0, ts = 0.0, emr = 0.0;
-  int cn = 0;
-  for (int i = 0; i < nwarps; ++i) {
-    kray += s_part[0][i];
-    ts += s_part[1][i];
-    emr += s_part[2][i];
-    cn += s_pcnt[i];
-  }
-  kray *= ct.tau_scale;
-  if (g == 0 && em != nullptr) {  // first channel block only: the ray's continuum images
-    em[ray] = emr * ct.em_scale;
-    kff[ray] = kray;
-    tsum[ray] = ts;
-    tcount[ray] = cn;
   }
 
   // K5 epilogue: rrls.py:444-447, physics.py:571-574, classes.py:1323-1328, :1484-1488
-  const double tmean = ts / (double)cn;
+  const int cn = rm.cnt;
+  const double kray = rm.kray;
+  const double tmean = rm.tsum / (double)cn;
   // exp(h nu_c / k Tmean) = exp(h nu0 / k Tmean) exp(x), x = h (nu_c - nu0) / k Tmean: one exp
   // per ray and a cubic when |x| <= 1e-3 for every channel (x^4 / 24 <= 4e-14)
   const double hkm = ln.h_over_k / tmean;
@@ -917,7 +1016,8 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
   for (int j = 0; j < GCH; ++j) {
     const int c = g + j * NT;
     if (c >= nchan) break;
-    if (tau_rrl) st_column(tau_rrl + (size_t)c * plane + cube_offset + ray, acc[j]);
+    if (tau_rrl) st_column(tau_rrl + (size_t)c * plane + cube_offset + ray,
+                           cn >= 0 ? acc[j] : dnan());
     if (flux_rrl) {
       double s = dnan();
       if (cn > 0) {
@@ -937,7 +1037,6 @@ integrate_line_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum
       st_column(flux_rrl + (size_t)c * plane + cube_offset + ray, s);
     }
   }
-  __syncthreads();   // s_part / the batch buffer are reused by the next ray
   }  // ray loop
   RJP_STAMP_END(0)
 }
@@ -1112,6 +1211,7 @@ static void set_carveouts() {
   const int pct = 75;
   cudaFuncSetAttribute(const_tiles_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   cudaFuncSetAttribute(continuum_rays_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(ray_prepare_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   carve_line<32, 16, true, 2>(pct);
   carve_line<32, 16, true, 4>(pct);
   carve_line<32, 16, true, 8>(pct);
@@ -1148,6 +1248,15 @@ static bool bulk_ok(const double* tau, const double* flux, size_t plane, size_t 
          (reinterpret_cast<uintptr_t>(flux) % 16 == 0);
 }
 
+// byte offset of the entry buffer inside the line-pass scratch (cursor, RayMeta[nray], entries)
+static long long line_entries_offset(long long nray) {
+  return (64 + nray * (long long)sizeof(RayMeta) + 255) / 256 * 256;
+}
+
+extern "C" long long rjp_launch_line_scratch_bytes(long long nray, long long max_cells) {
+  return line_entries_offset(nray) + max_cells * (long long)sizeof(LineEntry) + 256;
+}
+
 extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
                                     const rjp_continuum* ct, const rjp_cell* cells,
                                     const int32_t* extents, const int32_t* ray_list,
@@ -1157,7 +1266,8 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
                                     int contsub, double dn_max, double* tau_rrl,
                                     double* flux_rrl, long long cube_plane,
                                     long long cube_offset, const double* travel_cells,
-                                    const double* vlos_cells, cudaStream_t stream,
+                                    const double* vlos_cells, void* scratch,
+                                    long long max_cells, cudaStream_t stream,
                                     cudaStream_t stream2) {
   const CellGrids ov = {travel_cells, vlos_cells};
   const int nxs = m->x_hi - m->x_lo;
@@ -1208,8 +1318,24 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
     const_tiles_kernel<<<(unsigned)grid, 32 * warps, 0, stream>>>(job);
   }
   if (lines && !env_int("RJP_SKIP_LINES", 0)) {
-    // channel blocks of at most 8 * 256 channels per launch; the first one also writes the
-    // continuum images of its rays
+    // scratch layout: [0, 64) cursor of the entry buffer, then one RayMeta per slab ray, then
+    // max_cells entries of 80 bytes
+    if (scratch == nullptr || max_cells < 0) return RJP_ERR_ARG;
+    unsigned char* sc = static_cast<unsigned char*>(scratch);
+    unsigned long long* cursor = reinterpret_cast<unsigned long long*>(sc);
+    RayMeta* meta = reinterpret_cast<RayMeta*>(sc + 64);
+    unsigned char* entries = sc + line_entries_offset((long long)nray);
+    if (cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), ls) != cudaSuccess)
+      return RJP_ERR_CUDA;
+    // one CTA per listed ray when the caller knows their number, else a multiple of what fits
+    size_t grid_rays = n_hint > 0 ? (size_t)n_hint
+                                  : (size_t)sms * 8 * (size_t)env_int("RJP_GRID_FACTOR", 16);
+    if (grid_rays > nray) grid_rays = nray;
+    // K4a: prepare the cells of every jet-crossing ray, its continuum sums and image pixels
+    ray_prepare_kernel<<<(unsigned)grid_rays, 64, 0, ls>>>(
+        *m, *ep, *ct, ov, *ln, dn_max, c4, ex2, ray_list, n_active, cursor, max_cells, entries,
+        meta, em, kff, tsum, tcount);
+    // K4b: channel blocks of at most 8 * 256 channels per launch
     const int cblock = env_int("RJP_CHAN_BLOCK", GCH_MAX * LINE_THREADS);   // (experiments)
     for (int c0 = 0; c0 < nchan; c0 += cblock) {
       const int nc = (nchan - c0 < cblock) ? nchan - c0 : cblock;
@@ -1218,7 +1344,6 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
       const size_t off = (size_t)c0 * plane;
       double* t_out = tau_rrl ? tau_rrl + off : nullptr;
       double* f_out = flux_rrl ? flux_rrl + off : nullptr;
-      double* em_o = (c0 == 0) ? em : nullptr;
       // equally spaced channels (the normal case) take the register-lean instantiation
       const bool uni = ln->chan_step != 0.0;
       // threads x channels-per-thread: few channels (a rank of a channel-sharded run) take a
@@ -1235,14 +1360,9 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
       const int force_t = env_int("RJP_LINE_THREADS", 0);
       if (force_t > 0 && uni && force_t * GCH_MAX >= nc) { threads = force_t; gch = GCH_MAX; }
 #define RJP_LAUNCH_LINE(T, B, U, G)                                                           \
-  do {                                                                                        \
-    size_t grid_ = n_hint > 0 ? (size_t)n_hint                                                \
-                              : (size_t)sms * (B) * (size_t)env_int("RJP_GRID_FACTOR", 16);   \
-    if (grid_ > nray) grid_ = nray;                                                           \
-    integrate_line_kernel<T, B, U, G><<<(unsigned)grid_, threads, 0, ls>>>(                   \
-        *m, *ep, *ct, ov, *ln, cb, nc, c0, contsub, dn_max, c4, ex2, ray_list, n_active, em_o, \
-        kff, tsum, tcount, t_out, f_out, plane, coff);                                        \
-  } while (0)
+  integrate_line_kernel<T, B, U, G><<<(unsigned)grid_rays, threads, 0, ls>>>(                 \
+      *ln, cb, nc, c0, contsub, dn_max, entries, meta, ray_list, n_active, t_out, f_out,      \
+      plane, coff)
       if (threads <= 32 && uni) {
         if (gch == 2) RJP_LAUNCH_LINE(32, 16, true, 2);
         else if (gch == 4) RJP_LAUNCH_LINE(32, 16, true, 4);

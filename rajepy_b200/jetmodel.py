@@ -753,6 +753,7 @@ class JetModel:
         _cabi.check(st, "rjp_ray_list")
         _launched(2)
         d["rays"], d["n_active_dev"], d["n_active_host"] = rays, n_act, None
+        d["ray_cells_host"] = None
         d["ray_meta"] = None
 
     def _n_active(self):
@@ -760,10 +761,15 @@ class JetModel:
         built)."""
         d = self._ensure_filled()
         if d["n_active_host"] is None:
-            d["n_active_host"] = int(d["n_active_dev"].item())
+            torch = _torch()
+            ext = d["extents"]
+            cells = (ext[:, 1] - ext[:, 0]).clamp_min(0).sum(dtype=torch.int64)
+            both = torch.stack([d["n_active_dev"][0].to(torch.int64), cells]).cpu()
+            d["n_active_host"], d["ray_cells_host"] = int(both[0]), int(both[1])
             if len(_N_ACTIVE) > 256:
                 _N_ACTIVE.clear()
-            _N_ACTIVE[self._geometry_key()] = d["n_active_host"]
+            if not d.get("custom_fill"):
+                _N_ACTIVE[self._geometry_key()] = (d["n_active_host"], d["ray_cells_host"])
         return d["n_active_host"]
 
     def _geometry_key(self):
@@ -778,13 +784,18 @@ class JetModel:
         first model of a geometry reads it back once, later ones (time series, repeated runs)
         never wait for the device.  The kernel itself reads the true count on the device, so a
         stale hint could only cost time, not correctness."""
+        return self._ray_counts()[0]
+
+    def _ray_counts(self):
+        """(jet-crossing rays, summed lengths of their extents) of the slab, from the
+        per-geometry memory when this geometry has been filled before (see _n_active_hint)."""
         d = self._dev
-        if d["n_active_host"] is not None:
-            return d["n_active_host"]
-        if self._overrides:            # user grids may empty cells: do not trust the cache
-            return self._n_active()
-        hit = _N_ACTIVE.get(self._geometry_key())
-        return hit if hit is not None else self._n_active()
+        if d["n_active_host"] is None:
+            hit = None if d.get("custom_fill") else _N_ACTIVE.get(self._geometry_key())
+            if hit is not None:
+                return hit
+            self._n_active()
+        return d["n_active_host"], d["ray_cells_host"]
 
     def _decide_ties(self, I, J, K, dec):
         """{flat slab cell index: change of its vertex count} from the reference's own numpy
@@ -885,7 +896,11 @@ class JetModel:
                                      d["cells"].data_ptr(), d["bricks"].data_ptr(),
                                      d["extents"].data_ptr(), self._stream())
             _cabi.check(st, "rjp_patch_cells")
-        _launched()
+            _launched()
+            # cells entered / left the jet: the ray list of the model's own fill is stale
+            d["custom_fill"] = True
+            with torch.cuda.device(d["device"]):
+                self._build_ray_list()
         self._fields.clear()
         self._cont = self._line = None
 
@@ -1084,7 +1099,7 @@ class JetModel:
                                        d["n_active_dev"].data_ptr(), 0,
                                        em.data_ptr(), kff.data_ptr(),
                                        tsum.data_ptr(), cnt.data_ptr(), None, None, 0, 1,
-                                       None, None, 0, 0, *self._cell_grid_ptrs(),
+                                       None, None, 0, 0, *self._cell_grid_ptrs(), None, 0,
                                        self._stream(), None)
             else:
                 c_lo, c_hi = 0, len(freqs)
@@ -1107,9 +1122,12 @@ class JetModel:
                     flux = torch.empty((nch, rows, nz), dtype=torch.float64, device=dev)
                 side = self._fill_remote_constants(tau, flux) if self._world > 1 else None
                 lines = nch > 0       # (more ranks than channels: continuum sums only)
+                n_hint, max_cells = self._ray_counts()
+                scratch = torch.empty(int(lib.rjp_line_scratch_bytes(d["model"], max_cells)),
+                                      dtype=torch.uint8, device=dev)
                 st = lib.rjp_integrate(d["model"], ep, ct, d["cells"].data_ptr(),
                                        d["extents"].data_ptr(), d["rays"].data_ptr(),
-                                       d["n_active_dev"].data_ptr(), self._n_active_hint(),
+                                       d["n_active_dev"].data_ptr(), n_hint,
                                        em.data_ptr(), kff.data_ptr(),
                                        tsum.data_ptr(), cnt.data_ptr(),
                                        ln if lines else None, chans if lines else None,
@@ -1117,13 +1135,16 @@ class JetModel:
                                        tau.data_ptr() if (want_tau and lines) else None,
                                        flux.data_ptr() if (want_flux and lines) else None,
                                        plane, coff, *self._cell_grid_ptrs(),
+                                       scratch.data_ptr(), max_cells,
                                        self._stream(), d["stream2"].cuda_stream)
+                scratch.record_stream(d["stream2"])
                 if self._world > 1:
                     _cabi.check(st, "rjp_integrate")
                     self._exchange_cubes(tau, flux, side)
                 del keep
             _cabi.check(st, "rjp_integrate")
-            _launched(2 if line is None else 1 + (len(freqs) + 2047) // 2048)
+            # writer + (ray walk | prepare + channel-loop launches)
+            _launched(2 if line is None else 2 + (len(freqs) + 2047) // 2048)
         self._cont = {"key": key_c, "em": em, "kff": kff, "tsum": tsum, "cnt": cnt}
         if line is not None:
             self._line = {"key": key_l, "tau": tau, "flux": flux, "c_lo": c_lo, "c_hi": c_hi}

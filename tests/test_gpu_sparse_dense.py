@@ -30,7 +30,7 @@ def test_sparse_walk_equals_dense_sweep(name):
                            d["cells"].data_ptr(), None, None, None, 0, em.data_ptr(),
                            kff.data_ptr(),
                            tsum.data_ptr(), cnt.data_ptr(), None, None, 0, 1, None, None,
-                           0, 0, None, None, jm._stream(), None)
+                           0, 0, None, None, None, 0, jm._stream(), None)
     _cabi.check(st, "rjp_integrate(dense)")
     torch.cuda.synchronize()
     assert torch.equal(cnt, sparse["cnt"])
