@@ -46,7 +46,9 @@ __device__ __forceinline__ unsigned long long gtime() {
 constexpr int ZT = 32;          // rays per CTA of the dense sweep
 constexpr int RPW = 8;          // rows in flight per warp
 // tuning knobs of the channel loop (measured on B200, profiles/README.md: 8 channels per
-// thread and 8 CTAs of 64 threads per SM beat 4 channels / 96-register variants)
+// thread; 12 CTAs of 64 threads per SM at 80 registers -- 8 / 9 / 10 / 14 / 16 CTAs per SM:
+// 4.79 / 4.62 / 4.60 / 4.43 / 4.51 ms against 4.39 -- since the per-cell preparation moved
+// into its own kernel)
 #ifndef RJP_GCH
 #define RJP_GCH 8
 #endif
@@ -726,7 +728,7 @@ struct RayMeta {
 };
 static_assert(sizeof(RayMeta) == 40, "RayMeta layout");
 
-// One CTA per jet-crossing ray: every thread prepares one cell of the extent per batch --
+// One CTA (one warp) per jet-crossing ray: every thread prepares one cell of the extent per batch --
 // burst factor, Doppler shift, widths, amplitude, class (decode / make_entry / to_fast: ~1500
 // dependent fp64 instructions per cell, latency-bound) -- and stores the 80-byte entry; the same
 // walk yields the ray's continuum sums (EM, K, sum T, count) and writes its pixels of the four
@@ -734,15 +736,20 @@ static_assert(sizeof(RayMeta) == 40, "RayMeta layout");
 // where its stalled warps took a third of that kernel's warp residency (ncu: 35 % of the stall
 // samples on 16 % of the instructions); as a kernel of its own it is hidden behind thousands of
 // independent rays, and the channel loop kernel is nothing but the channel loop.
+// one warp per ray, 32 CTAs per SM: most rays have fewer than 64 cells, and what this kernel
+// needs is many independent warps (measured: 64 threads x 8 CTAs 0.71 ms, x 16 0.57, this 0.5)
 #ifndef RJP_PREP_MINB
-#define RJP_PREP_MINB 16
+#define RJP_PREP_MINB 32
 #endif
-__global__ void __launch_bounds__(64, RJP_PREP_MINB)
+#ifndef RJP_PREP_THREADS
+#define RJP_PREP_THREADS 32
+#endif
+__global__ void __launch_bounds__(RJP_PREP_THREADS, RJP_PREP_MINB)
 ray_prepare_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct,
                    const CellGrids ov, const rjp_line ln, const double dn_max,
                    const double2* __restrict__ cells, const int2* __restrict__ extents,
                    const int32_t* __restrict__ ray_list,
-                   const int32_t* __restrict__ n_active_dev,
+                   const int32_t* __restrict__ n_active_dev, const int t0, const int t1,
                    unsigned long long* __restrict__ cursor, const long long capacity,
                    unsigned char* __restrict__ entries, RayMeta* __restrict__ meta,
                    double* __restrict__ em, double* __restrict__ kff,
@@ -758,8 +765,8 @@ ray_prepare_kernel(const rjp_model m, const rjp_epoch ep, const rjp_continuum ct
   __syncthreads();
   const int NT = blockDim.x;
   const int g = threadIdx.x, lane = g & 31, wrp = g >> 5, nwarps = NT >> 5;
-  const int n_active = *n_active_dev;
-  for (int ticket = blockIdx.x; ticket < n_active; ticket += gridDim.x) {
+  const int n_active = min(*n_active_dev, t1);     // this launch: rays [t0, t1) of the list
+  for (int ticket = t0 + blockIdx.x; ticket < n_active; ticket += gridDim.x) {
     const int ray = ray_list[ticket];              // slab-local ray index = xl * nz + iz
     const int2 ext = extents[ray];
     const int len = ext.y - ext.x;
@@ -887,7 +894,7 @@ integrate_line_kernel(const rjp_line ln, const rjp_channels ch, const int nchan,
                       const unsigned char* __restrict__ entries,
                       const RayMeta* __restrict__ meta,
                       const int32_t* __restrict__ ray_list,
-                      const int32_t* __restrict__ n_active_dev,
+                      const int32_t* __restrict__ n_active_dev, const int t0, const int t1,
                       double* __restrict__ tau_rrl, double* __restrict__ flux_rrl,
                       const size_t plane, const size_t cube_offset) {
   // one chunk of prepared cells (80 bytes each; +3 zero-amplitude pads for the 4-cell batches
@@ -904,7 +911,7 @@ integrate_line_kernel(const rjp_line ln, const rjp_channels ch, const int nchan,
   asm volatile("" : "+r"(tab));  // keep it in a register (rematerialising costs S2R + LEA)
   const int NT = blockDim.x;
   const int g = threadIdx.x;
-  const int n_active = *n_active_dev;
+  const int n_active = min(*n_active_dev, t1);     // this launch: rays [t0, t1) of the list
 
   // thread g owns channels g, g + NT, g + 2 NT, ...: at every step the lanes of a warp hold
   // 32 neighbouring channels, i.e. nearly the same point of the line profile, so the
@@ -935,7 +942,7 @@ integrate_line_kernel(const rjp_line ln, const rjp_channels ch, const int nchan,
   // exactly-resident CTAs pulling rays from a ticket counter is 7 % SLOWER (5.61 vs 5.25 ms at
   // 1024^2 rays x 512 channels) -- CTAs of one age advance in lockstep, CTAs of mixed ages
   // overlap their start-up and epilogue latencies with the others' channel loop.
-  for (int ticket = blockIdx.x; ticket < n_active; ticket += gridDim.x) {
+  for (int ticket = t0 + blockIdx.x; ticket < n_active; ticket += gridDim.x) {
   const RayMeta rm = meta[ticket];
   const int ray = ray_list[ticket];                // slab-local ray index = xl * nz + iz
   double acc[GCH];
@@ -1328,57 +1335,65 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
     if (cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), ls) != cudaSuccess)
       return RJP_ERR_CUDA;
     // one CTA per listed ray when the caller knows their number, else a multiple of what fits
-    size_t grid_rays = n_hint > 0 ? (size_t)n_hint
-                                  : (size_t)sms * 8 * (size_t)env_int("RJP_GRID_FACTOR", 16);
-    if (grid_rays > nray) grid_rays = nray;
-    // K4a: prepare the cells of every jet-crossing ray, its continuum sums and image pixels
-    ray_prepare_kernel<<<(unsigned)grid_rays, 64, 0, ls>>>(
-        *m, *ep, *ct, ov, *ln, dn_max, c4, ex2, ray_list, n_active, cursor, max_cells, entries,
-        meta, em, kff, tsum, tcount);
-    // K4b: channel blocks of at most 8 * 256 channels per launch
-    const int cblock = env_int("RJP_CHAN_BLOCK", GCH_MAX * LINE_THREADS);   // (experiments)
-    for (int c0 = 0; c0 < nchan; c0 += cblock) {
-      const int nc = (nchan - c0 < cblock) ? nchan - c0 : cblock;
-      rjp_channels cb = *ch;
-      cb.dnu += c0; cb.nu += c0; cb.cff += c0; cb.aff += c0; cb.bnu += c0;
-      const size_t off = (size_t)c0 * plane;
-      double* t_out = tau_rrl ? tau_rrl + off : nullptr;
-      double* f_out = flux_rrl ? flux_rrl + off : nullptr;
-      // equally spaced channels (the normal case) take the register-lean instantiation
-      const bool uni = ln->chan_step != 0.0;
-      // threads x channels-per-thread: few channels (a rank of a channel-sharded run) take a
-      // one-warp CTA with 2 / 4 / 8 channels per thread
-      int threads, gch = GCH_MAX;
-      if (uni && nc <= 32 * GCH_MAX) {
-        threads = 32;
-        gch = nc <= 64 ? 2 : (nc <= 128 ? 4 : 8);
-        if (GCH_MAX != 8) gch = GCH_MAX;
-      } else {
-        const int groups = (nc + GCH_MAX - 1) / GCH_MAX;
-        threads = ((groups + 31) / 32) * 32;
-      }
-      const int force_t = env_int("RJP_LINE_THREADS", 0);
-      if (force_t > 0 && uni && force_t * GCH_MAX >= nc) { threads = force_t; gch = GCH_MAX; }
+    const size_t grid_all = n_hint > 0 ? ((size_t)n_hint < nray ? (size_t)n_hint : nray)
+                                       : (size_t)sms * 8 * (size_t)env_int("RJP_GRID_FACTOR", 16);
+    // K4b for the rays [t0, t1) of the list: channel blocks of at most 8 * 256 channels
+    auto launch_line = [&](int t0, int t1, size_t grid_rays) {
+      const int cblock = env_int("RJP_CHAN_BLOCK", GCH_MAX * LINE_THREADS);   // (experiments)
+      for (int c0 = 0; c0 < nchan; c0 += cblock) {
+        const int nc = (nchan - c0 < cblock) ? nchan - c0 : cblock;
+        rjp_channels cb = *ch;
+        cb.dnu += c0; cb.nu += c0; cb.cff += c0; cb.aff += c0; cb.bnu += c0;
+        const size_t off = (size_t)c0 * plane;
+        double* t_out = tau_rrl ? tau_rrl + off : nullptr;
+        double* f_out = flux_rrl ? flux_rrl + off : nullptr;
+        // equally spaced channels (the normal case) take the register-lean instantiation
+        const bool uni = ln->chan_step != 0.0;
+        // threads x channels-per-thread: few channels (a rank of a channel-sharded run) take a
+        // one-warp CTA with 2 / 4 / 8 channels per thread
+        int threads, gch = GCH_MAX;
+        if (uni && nc <= 32 * GCH_MAX) {
+          threads = 32;
+          gch = nc <= 64 ? 2 : (nc <= 128 ? 4 : 8);
+          if (GCH_MAX != 8) gch = GCH_MAX;
+        } else {
+          const int groups = (nc + GCH_MAX - 1) / GCH_MAX;
+          threads = ((groups + 31) / 32) * 32;
+        }
+        const int force_t = env_int("RJP_LINE_THREADS", 0);
+        if (force_t > 0 && uni && force_t * GCH_MAX >= nc) { threads = force_t; gch = GCH_MAX; }
 #define RJP_LAUNCH_LINE(T, B, U, G)                                                           \
   integrate_line_kernel<T, B, U, G><<<(unsigned)grid_rays, threads, 0, ls>>>(                 \
-      *ln, cb, nc, c0, contsub, dn_max, entries, meta, ray_list, n_active, t_out, f_out,      \
-      plane, coff)
-      if (threads <= 32 && uni) {
-        if (gch == 2) RJP_LAUNCH_LINE(32, 16, true, 2);
-        else if (gch == 4) RJP_LAUNCH_LINE(32, 16, true, 4);
-        else RJP_LAUNCH_LINE(32, 16, true, 8);
-      } else if (threads <= 64) {
-        if (uni) RJP_LAUNCH_LINE(64, RJP_MINB64U, true, GCH_MAX);
-        else RJP_LAUNCH_LINE(64, RJP_MINB64, false, GCH_MAX);
-      } else if (threads <= 128) {
-        if (uni) RJP_LAUNCH_LINE(128, RJP_MINB128, true, GCH_MAX);
-        else RJP_LAUNCH_LINE(128, RJP_MINB128, false, GCH_MAX);
-      } else {
-        if (uni) RJP_LAUNCH_LINE(LINE_THREADS, 2, true, GCH_MAX);
-        else RJP_LAUNCH_LINE(LINE_THREADS, 2, false, GCH_MAX);
-      }
+      *ln, cb, nc, c0, contsub, dn_max, entries, meta, ray_list, n_active, t0, t1, t_out,     \
+      f_out, plane, coff)
+        if (threads <= 32 && uni) {
+          if (gch == 2) RJP_LAUNCH_LINE(32, 16, true, 2);
+          else if (gch == 4) RJP_LAUNCH_LINE(32, 16, true, 4);
+          else RJP_LAUNCH_LINE(32, 16, true, 8);
+        } else if (threads <= 64) {
+          if (uni) RJP_LAUNCH_LINE(64, RJP_MINB64U, true, GCH_MAX);
+          else RJP_LAUNCH_LINE(64, RJP_MINB64, false, GCH_MAX);
+        } else if (threads <= 128) {
+          if (uni) RJP_LAUNCH_LINE(128, RJP_MINB128, true, GCH_MAX);
+          else RJP_LAUNCH_LINE(128, RJP_MINB128, false, GCH_MAX);
+        } else {
+          if (uni) RJP_LAUNCH_LINE(LINE_THREADS, 2, true, GCH_MAX);
+          else RJP_LAUNCH_LINE(LINE_THREADS, 2, false, GCH_MAX);
+        }
 #undef RJP_LAUNCH_LINE
-    }
+      }
+    };
+    // K4a for the rays [t0, t1): per-cell line constants, continuum sums, image pixels
+    auto launch_prep = [&](int t0, int t1, size_t grid_rays, cudaStream_t st) {
+      ray_prepare_kernel<<<(unsigned)grid_rays, RJP_PREP_THREADS, 0, st>>>(
+          *m, *ep, *ct, ov, *ln, dn_max, c4, ex2, ray_list, n_active, t0, t1, cursor, max_cells,
+          entries, meta, em, kff, tsum, tcount);
+    };
+    // (Cutting the list into chunks so that the preparation of chunk k+1 runs beside the
+    // channel loop of chunk k was measured SLOWER: +0.05 ms per extra chunk at 67 048 rays x
+    // 512 channels -- every chunk pays its own tail.)
+    launch_prep(0, 2147483647, grid_all, ls);
+    launch_line(0, 2147483647, grid_all);
   } else {
     size_t grid = (nray + 7) / 8;
     if (grid > (size_t)sms * 8) grid = (size_t)sms * 8;

@@ -51,7 +51,7 @@ def main():
         jm._pass(line, chans, contsub=False)
 
     def setenv(**kw):
-        for k in ("RJP_CHAN_BLOCK", "RJP_GRID_FACTOR", "RJP_WRITER_CTAS", "RJP_WRITER_WARPS", "RJP_NO_BULK", "RJP_WRITER_PER_SM", "RJP_SKIP_WRITER", "RJP_SKIP_LINES",
+        for k in ("RJP_PIPE_CHUNKS", "RJP_CHAN_BLOCK", "RJP_GRID_FACTOR", "RJP_WRITER_CTAS", "RJP_WRITER_WARPS", "RJP_NO_BULK", "RJP_WRITER_PER_SM", "RJP_SKIP_WRITER", "RJP_SKIP_LINES",
                   "RJP_LINE_THREADS", "RJP_FUSE_WRITER"):
             os.environ.pop(k, None)
         for k, v in kw.items():
