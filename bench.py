@@ -14,12 +14,14 @@ image epilogue.  Metric = dense cells x channels / step time (Gcell.channel/s).
   python bench.py --impl reference ...     the numpy restatement of the reference's own
                                            CPU path, timed on a bounded sample
 
-N > 1 (strong scaling: the 1024^3 x 528-channel workload is fixed): `--shard channel`
-(default) -- every rank holds the grid and integrates a contiguous block of the line cube's
-channels; cube planes stay with their rank (that is the FITS cube layout), continuum images
-are replicated, and the per-channel sky-summed fluxes (Pipeline's results['flux']) are
-all-gathered over NCCL inside the timed region.  `--shard x` -- work-balanced x-slabs with the
-sparse exchange of the jet-crossing cube columns, every rank ends up with the full cubes.
+N > 1 (strong scaling: the 1024^3 x 528-channel workload is fixed): `--shard tile` (default)
+-- work-balanced x-slabs: every rank fills and integrates its sky tile and keeps its tile of the
+cubes; the sky images are all-gathered and the per-channel sky-summed fluxes (Pipeline's
+results['flux']) all-reduced over NCCL inside the timed region; the host cube of the e2e leg is
+assembled by channel blocks after an all-to-all of the packed jet-crossing columns.
+`--shard channel` -- every rank holds the grid and integrates a block of the cube's channels.
+`--shard x` -- x-slabs with the sparse exchange of the jet-crossing cube columns, every rank
+ends up with the full cubes on its device.
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over
 ranks.  After the timed region rank 0 recomputes the products unsharded and reports
 `sharded_equals_single`.  L2: every step writes 8.6 GB of cube output (and the grid
@@ -236,10 +238,14 @@ def run_reference(args):
 def bench_config(args):
     shard = "none"
     if args.gpus > 1:
-        shard = ("channel blocks: every rank integrates nchan/N channels of the cube on the "
-                 "whole grid and keeps its planes; continuum images replicated; all-gather of "
-                 "the per-channel sky-summed fluxes") if args.shard == "channel" else \
-                "work-balanced x-slabs, sparse exchange of the jet-crossing cube columns"
+        shard = {"channel": "channel blocks: every rank integrates nchan/N channels of the cube "
+                            "on the whole grid and keeps its planes; continuum images "
+                            "replicated; all-gather of the per-channel sky-summed fluxes",
+                 "tile": "work-balanced x-slabs (sky tiles): every rank fills and integrates its "
+                         "slab and keeps its tile of the cubes; all-gather of the sky images, "
+                         "all-reduce of the per-channel sky-summed fluxes",
+                 "x": "work-balanced x-slabs, sparse exchange of the jet-crossing cube columns: "
+                      "full cubes on every rank"}[args.shard]
     return {"workload": f"BASELINE configs[4]: example jet, {args.grid}^3 grid, c_size 0.5 au, "
                         f"epoch 1 yr, 16 continuum freqs 1-300 GHz + {args.nchan}-channel "
                         f"H58a cube (chan 100 kHz), contsub=False",
@@ -427,6 +433,11 @@ def run_gpu(args):
                 lo, hi = res["c_lo"], res["c_hi"]
                 mine = {k: res[k].view(hi - lo, -1) for k in ("tau", "flux")}
                 full = {k: rres[k].view(len(chans), -1)[lo:hi] for k in ("tau", "flux")}
+            elif axis == "tile":
+                lo, hi = jm.slab
+                mine = {k: res[k].view(len(chans), -1) for k in ("tau", "flux")}
+                full = {k: rres[k].view(len(chans), args.grid, args.grid)[:, lo:hi].reshape(
+                    len(chans), -1) for k in ("tau", "flux")}
             else:
                 mine = {k: res[k].view(len(chans), -1) for k in ("tau", "flux")}
                 full = {k: rres[k].view(len(chans), -1) for k in ("tau", "flux")}
@@ -457,8 +468,9 @@ def run_gpu(args):
                                    "all-gathered per-channel flux totals of ALL ranks against "
                                    "an unsharded model on rank 0's GPU (bars: 1e-6 on the "
                                    "cubes like the parity bar, 1e-9 on the totals and on "
-                                   "the continuum images).  x-slabs run the same kernels on "
-                                   "the same rays: bit-identical.  Channel blocks use another "
+                                   "the continuum images).  x-slabs / tiles run the same "
+                                   "kernels on the same rays: bit-identical cubes (the totals "
+                                   "are summed in another order).  Channel blocks use another "
                                    "thread layout than the 512-channel kernel: the cells of a "
                                    "ray are summed in another order (last bits) and single "
                                    "Voigt evaluations may differ by an fp32 rounding"}
@@ -592,7 +604,7 @@ def main():
     ap.add_argument("--nchan", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config4", action="store_true")
-    ap.add_argument("--shard", default="channel", choices=["channel", "x"],
+    ap.add_argument("--shard", default="tile", choices=["tile", "channel", "x"],
                     help="N > 1: how the cube is sharded")
     args = ap.parse_args()
     if args.impl == "reference":

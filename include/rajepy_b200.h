@@ -271,6 +271,12 @@ int rjp_integrate(const rjp_model* m_host, const rjp_epoch* ep_host,
  *                    light != 0: a small grid meant to run on a side stream beside a long
  *                    channel loop; 0: a grid that reaches the HBM write bandwidth alone.
  * ray_ids index into a plane (global ray = x * nz + z for a full-size cube).          */
+/* totals[c] = sum over the listed rays of cube[c * cube_plane + cube_offset + ray], NaN skipped:
+ * the sky-summed flux of every channel (Pipeline's results['flux'], classes.py:2468-2472) --
+ * every other ray of a line cube holds the constant 0 / NaN.  Deterministic summation order. */
+int rjp_column_totals(const double* cube, int64_t cube_plane, int64_t cube_offset,
+                      const int32_t* ray_list, const int32_t* n_active, int32_t nchan,
+                      double* totals, void* stream);
 int rjp_pack_rays(const double* cube, int64_t cube_plane, const int32_t* ray_ids, int32_t n,
                   int32_t n_stride, int32_t nchan, double* out, void* stream);
 int rjp_scatter_rays(const double* in, int32_t n_stride, const int32_t* ray_ids, int32_t n,

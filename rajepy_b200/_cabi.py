@@ -66,7 +66,8 @@ EXPORTS = ("rjp_strerror", "rjp_last_cuda_error", "rjp_abi_version", "rjp_struct
            "rjp_fill_grid", "rjp_patch_cells", "rjp_cell_field", "rjp_ray_list", "rjp_integrate",
            "rjp_continuum_images", "rjp_voigt_profile", "rjp_brick_count", "rjp_pack_rays",
            "rjp_scatter_rays", "rjp_fill_missed", "rjp_los_means", "rjp_override_cells",
-           "rjp_ray_list_chunks", "rjp_host_assemble", "rjp_line_scratch_bytes")
+           "rjp_ray_list_chunks", "rjp_host_assemble", "rjp_line_scratch_bytes",
+           "rjp_column_totals")
 
 ABI_VERSION = 5      # RJP_ABI_VERSION of include/rajepy_b200.h this binding was written for
 
@@ -130,6 +131,8 @@ def load():
     lib.rjp_line_scratch_bytes.argtypes = [C.POINTER(Model), i64]
     lib.rjp_line_scratch_bytes.restype = i64
     lib.rjp_pack_rays.argtypes = [vp, i64, vp, i32, i32, i32, vp, vp]
+    lib.rjp_column_totals.argtypes = [vp, i64, i64, vp, vp, i32, vp, vp]
+    lib.rjp_column_totals.restype = C.c_int
     lib.rjp_scatter_rays.argtypes = [vp, i32, vp, i32, i32, vp, i64, vp]
     lib.rjp_fill_missed.argtypes = [vp, i64, i32, i64, i64, i64, i64, vp, vp, i32, vp]
     lib.rjp_continuum_images.argtypes = [vp, vp, vp, i64, vp, vp, dbl, i32, vp, vp, vp, vp]

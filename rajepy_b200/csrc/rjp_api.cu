@@ -26,6 +26,8 @@ int rjp_launch_pack_rays(const double*, long long, const int32_t*, int, int, int
                          cudaStream_t);
 int rjp_launch_scatter_rays(const double*, int, const int32_t*, int, int, double*, long long,
                             cudaStream_t);
+int rjp_launch_column_totals(const double*, long long, long long, const int32_t*, const int32_t*,
+                             int, double*, cudaStream_t);
 int rjp_launch_ray_list(const int32_t*, int, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int rjp_ray_list_chunk(void);
 int rjp_launch_continuum_images(const double*, const double*, const int32_t*, int64_t,
@@ -201,6 +203,16 @@ extern "C" int rjp_fill_missed(const int32_t* extents, int64_t nray, int32_t nch
   return check_launch(rjp_launch_fill_missed(extents, nray, nchan, cube_plane, cube_offset,
                                              skip_lo, skip_hi, tau, flux, light,
                                              (cudaStream_t)stream));
+}
+
+extern "C" int rjp_column_totals(const double* cube, int64_t cube_plane, int64_t cube_offset,
+                                 const int32_t* ray_list, const int32_t* n_active,
+                                 int32_t nchan, double* totals, void* stream) {
+  if (nchan < 0 || cube_plane <= 0 || cube_offset < 0 ||
+      (nchan > 0 && (!cube || !ray_list || !n_active || !totals)))
+    return RJP_ERR_ARG;
+  return check_launch(rjp_launch_column_totals(cube, cube_plane, cube_offset, ray_list, n_active,
+                                               nchan, totals, (cudaStream_t)stream));
 }
 
 extern "C" int rjp_pack_rays(const double* cube, int64_t cube_plane, const int32_t* ray_ids,

@@ -537,6 +537,33 @@ __global__ void scatter_rays_kernel(const double* __restrict__ in, int n_stride,
   }
 }
 
+// Per-channel sum over the sky of a cube, NaN skipped (Pipeline's results['flux'] of a line
+// run, classes.py:2468-2472): only the columns of the listed rays can hold anything but the
+// constant 0 / NaN, so one CTA per channel gathers those (ordered list: neighbouring lanes read
+// neighbouring rays) and reduces them in a fixed order.
+__global__ void __launch_bounds__(256)
+column_totals_kernel(const double* __restrict__ cube, size_t plane, size_t offset,
+                     const int32_t* __restrict__ ray_list,
+                     const int32_t* __restrict__ n_active_dev, double* __restrict__ totals) {
+  __shared__ double s_w[8];
+  const int n = *n_active_dev;
+  const double* p = cube + (size_t)blockIdx.x * plane + offset;
+  double sum = 0.0;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const double v = p[ray_list[k]];
+    if (v == v) sum += v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_w[w];
+    totals[blockIdx.x] = t;
+  }
+}
+
 // Continuum-only walk: one warp per jet-crossing ray, lanes stride along the extent.  The
 // number of listed rays is read on the device (the host never waits for it); warps stride
 // over the list.
@@ -1316,7 +1343,18 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
   if (!env_int("RJP_SKIP_WRITER", 0)) {   // (debug knob: time the ray kernels alone)
     // beside a channel loop: few CTAs of several warps, so that only a few SMs give up a
     // slot of the (register-bound) channel loop; alone: one CTA of 4 warps on every SM
-    const int ctas = env_int("RJP_WRITER_CTAS", lines ? sms / 4 : sms);
+    // With few rays to walk (the outer slabs of a sharded run hold mostly empty sky) the
+    // writer is the longer of the two: size it so that it ends with the channel loop
+    // (measured: ~57 GB/s per CTA of 4 warps, ~6.6e-5 ms per ray x channel of the loop).
+    int ctas_auto = sms / 4;
+    if (lines) {
+      const double t_loop_ms = 6.6e-5 * (double)(n_hint > 0 ? n_hint : (int)(nray / 16)) *
+                               (double)nchan / 512.0 * 8.0;
+      const double bytes = 16.0 * (double)nray * (double)nchan;
+      const double want = bytes / 57e6 / (t_loop_ms > 0.05 ? t_loop_ms : 0.05);
+      if (want > ctas_auto) ctas_auto = want < sms ? (int)want : sms;
+    }
+    const int ctas = env_int("RJP_WRITER_CTAS", lines ? ctas_auto : sms);
     const int warps = env_int("RJP_WRITER_WARPS", 4);
     const size_t ntiles = (nray + CT_TILE - 1) / CT_TILE;
     const size_t items = ntiles * (size_t)(lines ? (nchan + RJP_CT_CG - 1) / RJP_CT_CG : 1);
@@ -1437,6 +1475,15 @@ extern "C" int rjp_launch_fill_missed(const int32_t* extents, long long nray, in
                   (size_t)skip_hi,
                   bulk_ok(tau, flux, (size_t)plane, (size_t)offset, (size_t)nray) ? 1 : 0};
   const_tiles_kernel<<<(unsigned)grid, 32 * warps, 0, stream>>>(job);
+  return RJP_OK;
+}
+
+extern "C" int rjp_launch_column_totals(const double* cube, long long plane, long long offset,
+                                        const int32_t* ray_list, const int32_t* n_active,
+                                        int nchan, double* totals, cudaStream_t stream) {
+  if (nchan <= 0) return RJP_OK;
+  column_totals_kernel<<<nchan, 256, 0, stream>>>(cube, (size_t)plane, (size_t)offset, ray_list,
+                                                  n_active, totals);
   return RJP_OK;
 }
 

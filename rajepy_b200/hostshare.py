@@ -51,11 +51,13 @@ class Segment:
             raise RuntimeError(f"cudaHostRegister of {hi - lo} bytes failed ({err})")
         self.registered[(offset, nbytes)] = lo
 
-    def tensor(self, offset, shape):
-        """float64 torch view of `shape` at byte `offset`, page-locked."""
+    def tensor(self, offset, shape, pin=True):
+        """float64 torch view of `shape` at byte `offset`; page-locked for this process's GPU
+        unless `pin` is False (host threads are the only writers)."""
         import torch
         n = int(np.prod(shape))
-        self._register(offset, 8 * n)
+        if pin:
+            self._register(offset, 8 * n)
         view = self._np[offset: offset + 8 * n].view(np.float64).reshape(shape)
         return torch.from_numpy(view)
 

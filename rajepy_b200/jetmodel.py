@@ -247,8 +247,13 @@ class JetModel:
         self._device_arg = device
         if shard is None:
             shard = (0, 1)
-        if shard_axis not in ('x', 'channel'):
-            raise ValueError("shard_axis must be 'x' or 'channel'")
+        if shard_axis not in ('x', 'tile', 'channel'):
+            raise ValueError("shard_axis must be 'x', 'tile' or 'channel'")
+        # 'tile': x-slabs like 'x', but the line cubes STAY sky tiles (nchan, nx_slab, nz) on
+        # their ranks -- nothing but the small sky images and per-channel totals is exchanged on
+        # the device; a host cube is assembled through an all-to-all of the packed jet-crossing
+        # columns (`_host_cube`).  'x' completes full-size cubes on every rank.
+        self._tiles = shard_axis == 'tile'
         # shard_axis='channel': every rank holds the whole grid and integrates a contiguous
         # block of the channels of a line cube (sharding.chan_bounds); continuum products are
         # replicated, cube planes stay with their rank (no exchange).  'x': x-slabs.
@@ -299,8 +304,12 @@ class JetModel:
         with np.errstate(all="ignore"):
             inside = (w <= hm.w_r(r, g["w_0"], g["mod_r_0"], g["r_0"], g["epsilon"])) & \
                      (np.abs(r) >= g["r_0"])
-        coarse = inside.sum(axis=(1, 2)).astype(np.float64)
+        coarse = inside.sum(axis=(1, 2)).astype(np.float64) * (sx * sy * sz) / sx
         out = np.interp(np.arange(nx), ix, coarse)
+        # a plane of empty sky is not free either: its rows of every cube plane are constants
+        # to be written (16 B per ray and channel at ~5.4 TB/s, against ~1.05 ns per in-jet cell
+        # and 512 channels of the channel loop: ~1.45 in-jet cells per ray)
+        out = out + 1.45 * nz
         if len(_PLANE_WEIGHTS) > 32:
             _PLANE_WEIGHTS.clear()
         _PLANE_WEIGHTS[key] = out
@@ -1114,13 +1123,14 @@ class JetModel:
                 nch = len(freqs)
                 # sharded: every rank writes its slab straight into full-size cubes; the
                 # other slabs arrive through the sparse exchange below
-                rows = self._nx if self._world > 1 else nxs
-                plane, coff = (self._nx * nz, self._x_lo * nz) if self._world > 1 else (0, 0)
+                full = self._world > 1 and not self._tiles
+                rows = self._nx if full else nxs
+                plane, coff = (self._nx * nz, self._x_lo * nz) if full else (0, 0)
                 if want_tau:
                     tau = torch.empty((nch, rows, nz), dtype=torch.float64, device=dev)
                 if want_flux:
                     flux = torch.empty((nch, rows, nz), dtype=torch.float64, device=dev)
-                side = self._fill_remote_constants(tau, flux) if self._world > 1 else None
+                side = self._fill_remote_constants(tau, flux) if full else None
                 lines = nch > 0       # (more ranks than channels: continuum sums only)
                 n_hint, max_cells = self._ray_counts()
                 scratch = torch.empty(int(lib.rjp_line_scratch_bytes(d["model"], max_cells)),
@@ -1138,7 +1148,7 @@ class JetModel:
                                        scratch.data_ptr(), max_cells,
                                        self._stream(), d["stream2"].cuda_stream)
                 scratch.record_stream(d["stream2"])
-                if self._world > 1:
+                if full:
                     _cabi.check(st, "rjp_integrate")
                     self._exchange_cubes(tau, flux, side)
                 del keep
@@ -1233,9 +1243,10 @@ class JetModel:
         """Device tile(s) -> full host numpy array, all-gathering x-slabs if sharded."""
         nxs, nz = self._x_hi - self._x_lo, self._nz
         wanted = self._host_ranks is None or self._rank in self._host_ranks
-        if lead is not None and self._world > 1 and t.numel() == lead * self._nx * nz:
-            # cube completed by _exchange_cubes
-            return _to_host(t.view(lead, self._nx, nz)) if wanted else None
+        if self._world > 1 and t.numel() == (lead or 1) * self._nx * nz:
+            # already complete (cube finished by _exchange_cubes, images from _sky_sums)
+            shape = (self._nx, nz) if lead is None else (lead, self._nx, nz)
+            return _to_host(t.view(shape)) if wanted else None
         t = t.view(nxs, nz) if lead is None else t.view(lead, nxs, nz)
         if self._world > 1:
             t = gather_x(t, self._nx, self._rank, self._world, dim=0 if lead is None else 1,
@@ -1255,6 +1266,8 @@ class JetModel:
         wanted = self._host_ranks is None or self._rank in self._host_ranks
         if self._chan_world > 1:
             return self._shared_cube(cube, fill, nch, sibling)
+        if self._tiles and self._world > 1:
+            return self._shared_cube_from_tiles(cube, fill, nch)
         if self._world > 1 or cube.numel() != nch * plane:
             return self._host_image(cube, lead=nch)
         out = torch.empty((nch, plane), dtype=torch.float64, pin_memory=True)
@@ -1367,12 +1380,84 @@ class JetModel:
             return None
         return seg.array((nch, self._nx, self._nz))
 
+    def _shared_cube_from_tiles(self, cube, fill, nch):
+        """Tile-sharded hand-over.  The ranks hold sky tiles (nch, nx_slab, nz); the host cube is
+        assembled by CHANNEL blocks (an even share of the host work whatever the slabs look
+        like): one all-to-all over NVLink moves the packed columns of the jet-crossing rays --
+        the only data that differs from the constant -- from the rank that integrated the ray
+        to the rank that assembles the channel; then every rank copies its block's columns to the
+        host and writes its planes of the shared cube (constants + columns)."""
+        import torch.distributed as dist
+        from . import hostshare
+        from .sharding import chan_bounds
+        torch = _torch()
+        lib = _cabi.load()
+        d = self._dev
+        dev = d["device"]
+        world, rank = self._world, self._rank
+        nxs, nz = self._x_hi - self._x_lo, self._nz
+        plane_tile, plane = nxs * nz, self._nx * nz
+        n = self._n_active()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            # who lists how many rays, and which (global ids, ascending: the slabs are ordered)
+            cnt = torch.tensor([n], dtype=torch.int64, device=dev)
+            cnts = torch.empty(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(cnts, cnt)
+            counts = [int(c) for c in cnts.cpu()]
+            n_all, nmax = sum(counts), max(max(counts), 1)
+            ids = torch.full((nmax,), -1, dtype=torch.int32, device=dev)
+            ids[:n] = d["rays"][:n] + self._x_lo * nz
+            all_ids = torch.empty((world, nmax), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(all_ids.view(-1), ids)
+            ids_all = torch.cat([all_ids[r, :counts[r]] for r in range(world)])
+            # own rays, all channels -> the channel blocks' owners
+            cols = torch.empty((nch, max(n, 1)), dtype=torch.float64, device=dev)
+            if n > 0:
+                _cabi.check(lib.rjp_pack_rays(cube.data_ptr(), plane_tile, d["rays"].data_ptr(),
+                                              n, n, nch, cols.data_ptr(), stream.cuda_stream),
+                            "rjp_pack_rays")
+                _launched()
+            blocks = [chan_bounds(nch, r, world) for r in range(world)]
+            c_lo, c_hi = blocks[rank]
+            nb = c_hi - c_lo
+            send = cols[:, :n].contiguous().view(-1) if n > 0 else cols.view(-1)[:0]
+            recv = torch.empty(nb * n_all, dtype=torch.float64, device=dev)
+            dist.all_to_all_single(recv, send,
+                                   output_split_sizes=[nb * c for c in counts],
+                                   input_split_sizes=[(hi - lo) * n for lo, hi in blocks])
+            # [source][channel][ray of source] -> (channel, all rays)
+            parts, off = [], 0
+            for c in counts:
+                parts.append(recv[off: off + nb * c].view(nb, c))
+                off += nb * c
+            mine = torch.cat(parts, dim=1).contiguous() if nb > 0 else recv.view(0, n_all)
+            ids_h = torch.empty(n_all, dtype=torch.int32, pin_memory=True)
+            ids_h.copy_(ids_all, non_blocking=True)
+            cols_h = torch.empty((nb, n_all), dtype=torch.float64, pin_memory=True)
+            cols_h.copy_(mine, non_blocking=True)
+            stream.synchronize()
+        seg = hostshare.segment(nch * plane * 8, rank)
+        if nb > 0:
+            out = seg.tensor(c_lo * plane * 8, (nb, plane), pin=False)
+            st = lib.rjp_host_assemble(out.data_ptr(), nb, plane, ids_h.data_ptr(), n_all,
+                                       cols_h.data_ptr(), n_all, float(fill), _host_threads())
+            _cabi.check(st, "rjp_host_assemble")
+        dist.barrier()
+        wanted = self._host_ranks is None or rank in self._host_ranks
+        if not wanted:
+            seg.release()
+            return None
+        return seg.array((nch, self._nx, nz))
+
     def _continuum_images_device(self, freqs, want):
         """K5 for a list of frequencies; `want` in ('tau', 'intensity', 'flux').
         Returns a device tensor (nfreq, nx_slab * nz)."""
         torch = _torch()
         lib = _cabi.load()
         c = self._pass()
+        if self._tiles and self._world > 1:
+            c = self._sky_sums()
         dev = c["em"].device
         freqs = np.atleast_1d(np.asarray(freqs, dtype=np.float64))
         nf = freqs.size
@@ -1399,6 +1484,24 @@ class JetModel:
             _cabi.check(st, "rjp_continuum_images")
             _launched()
         return out
+
+    def _sky_sums(self):
+        """Tile-sharded models: the four ray sums of the WHOLE sky (EM, K, sum T, count), from
+        one exchange of the slabs' tiles (29 MB at 1024^2 rays) -- every per-frequency image is
+        then formed locally instead of being gathered (16 frequencies x 2 products: 268 MB)."""
+        torch = _torch()
+        c = self._pass()
+        if c.get("sky") is None:
+            nxs, nz = self._x_hi - self._x_lo, self._nz
+            pack = torch.stack([c["em"], c["kff"], c["tsum"],
+                                c["cnt"].to(torch.float64)]).view(4, nxs, nz)
+            full = gather_x(pack, self._nx, self._rank, self._world, dim=1, bounds=self._bounds)
+            if hasattr(full, "contiguous"):
+                full = full.contiguous()
+            full = full.reshape(4, self._nx * nz)
+            c["sky"] = {"em": full[0], "kff": full[1], "tsum": full[2],
+                        "cnt": full[3].to(torch.int32)}
+        return c["sky"]
 
     def _continuum_images(self, freqs, want):
         out = self._continuum_images_device(freqs, want)
@@ -1449,7 +1552,8 @@ class JetModel:
             nch = len(chan_freqs)
         cont = self._pass()
         conv = self._host_image if host else self._device_image
-        out["em"] = conv(cont["em"])
+        out["em"] = conv(self._sky_sums()["em"] if (self._tiles and self._world > 1)
+                         else cont["em"])
         if cont_freqs is not None:
             nf = len(np.atleast_1d(cont_freqs))
             out["tau_ff"] = conv(self._continuum_images_device(cont_freqs, 'tau'), lead=nf)
@@ -1462,6 +1566,10 @@ class JetModel:
                 # channel-sharded: the planes [c_lo, c_hi) this rank integrated stay with it
                 out["tau_rrl"], out["flux_rrl"] = res["tau"], res["flux"]
                 out["channels"] = (res["c_lo"], res["c_hi"])
+            elif self._tiles and self._world > 1:
+                # sky tiles: rows [x_lo, x_hi) of every plane stay with this rank
+                out["tau_rrl"], out["flux_rrl"] = res["tau"], res["flux"]
+                out["rows"] = (self._x_lo, self._x_hi)
             else:
                 out["tau_rrl"] = conv(res["tau"], lead=nch)
                 out["flux_rrl"] = conv(res["flux"], lead=nch)
@@ -1548,8 +1656,8 @@ class JetModel:
 
     def _device_image(self, t, lead=None):
         nxs, nz = self._x_hi - self._x_lo, self._nz
-        if lead is not None and self._world > 1 and t.numel() == lead * self._nx * nz:
-            return t.view(lead, self._nx, nz)
+        if self._world > 1 and t.numel() == (lead or 1) * self._nx * nz:
+            return t.view((self._nx, nz) if lead is None else (lead, self._nx, nz))
         t = t.view(nxs, nz) if lead is None else t.view(lead, nxs, nz)
         if self._world > 1:
             t = gather_x(t, self._nx, self._rank, self._world, dim=0 if lead is None else 1,
@@ -1559,7 +1667,8 @@ class JetModel:
     # ------------------------------------------------------------------ public RT methods
     def emission_measure(self, savefits=False):
         """Emission measure viewed along the y-axis [pc cm^-6] (classes.py:1101-1128)"""
-        ems = self._host_image(self._pass()["em"])
+        ems = self._host_image(self._sky_sums()["em"] if (self._tiles and self._world > 1)
+                               else self._pass()["em"])
         if ems is None:
             return None
         if savefits:
@@ -1670,10 +1779,26 @@ class JetModel:
         freqs = np.atleast_1d(np.asarray(freq, dtype=np.float64))
         res = self._pass(rrl, freqs, contsub=contsub, want_tau=True, want_flux=True)
         flux = res["flux"]
-        local = torch.nansum(flux.reshape(flux.shape[0], -1), dim=1)
+        d = self._dev
+        lib = _cabi.load()
+        nloc = flux.shape[0]
+        local = torch.zeros(nloc, dtype=torch.float64, device=flux.device)
+        full = self._world > 1 and not self._tiles          # full-size cube, own rows only
+        plane = flux.numel() // max(nloc, 1)
+        if nloc > 0:
+            with torch.cuda.device(flux.device):
+                st = lib.rjp_column_totals(flux.data_ptr(), plane,
+                                           self._x_lo * self._nz if full else 0,
+                                           d["rays"].data_ptr(), d["n_active_dev"].data_ptr(),
+                                           nloc, local.data_ptr(), self._stream())
+                _cabi.check(st, "rjp_column_totals")
+                _launched()
         if self._chan_world > 1:
             from .sharding import gather_channel_totals
             local = gather_channel_totals(local, freqs.size, self._chan_rank, self._chan_world)
+        elif self._world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(local, op=dist.ReduceOp.SUM)      # the slabs partition the sky
         return local.cpu().numpy() if host else local
 
     def _cellwise_tau_rrl(self, rrl, freqs):

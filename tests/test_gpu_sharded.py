@@ -102,6 +102,33 @@ def _worker(rank, world, port, out_dir):
         ok = ok and tau is None and cube is None
     del tau, cube
     jm.release()
+    # sky tiles: the cubes stay tiles on the device (bit-identical rows of the single-GPU cube);
+    # the host cube is assembled by channel blocks after an all-to-all of the packed columns
+    jm = rb.JetModel(cases.with_grid(cases.base_params(), 64, 96, 128), log=log,
+                     device=f"cuda:{rank}", shard=(rank, world), shard_axis='tile',
+                     host_ranks=(0,))
+    jm.time = 0.9 * con.year
+    lo, hi = jm.slab
+    dev_res = jm.rt_products(freqs, 'H58a', chans, contsub=False, host=False)
+    ok = ok and dev_res["rows"] == (lo, hi)
+    tile = dev_res["flux_rrl"].view(len(chans), hi - lo, jm.nz).cpu().numpy()
+    ok = ok and np.array_equal(np.nan_to_num(tile), np.nan_to_num(res["one"][4][:, lo:hi]))
+    ok = ok and tuple(dev_res["flux_ff"].shape) == (2, jm.nx, jm.nz)     # complete sky images
+    ok = ok and np.array_equal(np.nan_to_num(dev_res["flux_ff"].cpu().numpy()),
+                               np.nan_to_num(res["one"][2]))
+    ok = ok and np.array_equal(dev_res["em"].cpu().numpy(), res["one"][1])
+    tot = jm.rrl_flux_totals('H58a', chans, contsub=False)
+    ok = ok and np.allclose(tot, want_tot, rtol=1e-12, atol=0)
+    tau = jm.optical_depth_rrl('H58a', chans)
+    cube = jm.flux_rrl('H58a', chans, contsub=False)
+    if rank == 0:
+        ok = ok and np.array_equal(tau, res["one"][3])
+        ok = ok and np.array_equal(np.nan_to_num(cube), np.nan_to_num(res["one"][4]))
+        ok = ok and np.array_equal(np.isnan(cube), np.isnan(res["one"][4]))
+    else:
+        ok = ok and tau is None and cube is None
+    del tau, cube
+    jm.release()
     open(os.path.join(out_dir, f"r{rank}.txt"), "w").write("ok" if ok else "MISMATCH")
     dist.barrier()
     dist.destroy_process_group()
