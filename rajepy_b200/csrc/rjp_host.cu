@@ -4,7 +4,7 @@
 // the packed columns of the jet-crossing rays (rjp_pack_rays) cross PCIe; this routine writes
 // the constants with streaming stores from several host threads and drops the columns in.
 // No CUDA calls here: plain C++ threads, compiled into the same library.
-#include <emmintrin.h>
+#include <immintrin.h>
 #include <stdint.h>
 #include <string.h>
 #include <thread>
@@ -15,8 +15,32 @@ namespace {
 
 struct Run { int64_t ray, k, len; };   // ray_ids[k .. k+len) = ray, ray+1, ...
 
+// 32-byte streaming stores where the CPU has AVX (checked once at run time)
+__attribute__((target("avx"))) void fill_stream_avx(double* p, int64_t n, double v) {
+  int64_t i = 0;
+  while (i < n && (reinterpret_cast<uintptr_t>(p + i) & 31)) p[i++] = v;
+  const __m256d vv = _mm256_set1_pd(v);
+  for (; i + 16 <= n; i += 16) {
+    _mm256_stream_pd(p + i, vv);
+    _mm256_stream_pd(p + i + 4, vv);
+    _mm256_stream_pd(p + i + 8, vv);
+    _mm256_stream_pd(p + i + 12, vv);
+  }
+  for (; i + 4 <= n; i += 4) _mm256_stream_pd(p + i, vv);
+  for (; i < n; ++i) p[i] = v;
+}
+
+inline bool have_avx() {
+  static const bool v = (__builtin_cpu_init(), __builtin_cpu_supports("avx") != 0);
+  return v;
+}
+
 // n doubles of `v` at p with non-temporal stores (no read-for-ownership of the destination)
 inline void fill_stream(double* p, int64_t n, double v) {
+  if (n >= 64 && have_avx()) {
+    fill_stream_avx(p, n, v);
+    return;
+  }
   if (n <= 0) return;
   if (n < 32) {
     for (int64_t i = 0; i < n; ++i) p[i] = v;
