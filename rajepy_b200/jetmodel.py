@@ -269,7 +269,11 @@ class JetModel:
         # the FITS files).  None = every rank, the drop-in behaviour.
         self._host_ranks = None if host_ranks is None else {int(r) for r in host_ranks}
         # x-slabs of equal estimated work (in-jet cells), not equal width: see _plane_weights
-        self._bounds = balanced_bounds(self._plane_weights(), self._world) \
+        # (a plane of empty sky is not free: its rows of every cube plane are constants to be
+        # written, 16 B per ray and channel at ~5.4 TB/s against ~1.05 ns per in-jet cell and
+        # 512 channels of the channel loop, i.e. ~1.45 in-jet cells per ray of the plane)
+        self._bounds = balanced_bounds(self._plane_weights(), self._world,
+                                       plane_cost=1.45 * self._nz) \
             if (balance and self._world > 1) else even_bounds(self._nx, self._world)
         self._x_lo, self._x_hi = self._bounds[self._rank]
         self._dev = None       # dict of device buffers once filled
@@ -306,10 +310,6 @@ class JetModel:
                      (np.abs(r) >= g["r_0"])
         coarse = inside.sum(axis=(1, 2)).astype(np.float64) * (sx * sy * sz) / sx
         out = np.interp(np.arange(nx), ix, coarse)
-        # a plane of empty sky is not free either: its rows of every cube plane are constants
-        # to be written (16 B per ray and channel at ~5.4 TB/s, against ~1.05 ns per in-jet cell
-        # and 512 channels of the channel loop: ~1.45 in-jet cells per ray)
-        out = out + 1.45 * nz
         if len(_PLANE_WEIGHTS) > 32:
             _PLANE_WEIGHTS.clear()
         _PLANE_WEIGHTS[key] = out

@@ -26,11 +26,16 @@ def slab_bounds(nx, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def balanced_bounds(weights, world):
-    """Contiguous x-slabs [(lo, hi)] * world with (nearly) equal summed `weights` (one weight
-    per x-plane, e.g. an estimate of the in-jet cells of the plane): the jet occupies a narrow
-    range of x, so equal-width slabs would leave most ranks without any ray to integrate, and
-    empty space costs nothing in the sparse fill / ray walk.  Every rank gets >= 1 plane."""
+def balanced_bounds(weights, world, plane_cost=0.0):
+    """Contiguous x-slabs [(lo, hi)] * world that minimise the cost of the most expensive slab,
+    cost(slab) = max(sum of `weights` over its planes, plane_cost * number of planes).
+
+    `weights`: one per x-plane, an estimate of its in-jet cells (the ray walk / channel loop).
+    `plane_cost`: what a plane costs even when it is empty sky -- its rows of constants in
+    every cube plane -- in the same unit.  The two run side by side on a GPU (channel loop and
+    constant writer), hence the max, not the sum.  The jet occupies a narrow range of x, so
+    equal-width slabs would leave most ranks without any ray to integrate.  Every rank gets
+    >= 1 plane."""
     import numpy as np
     w = np.asarray(weights, dtype=np.float64)
     nx = w.size
@@ -38,13 +43,32 @@ def balanced_bounds(weights, world):
         raise ValueError("more ranks than x-planes")
     w = w + max(w.sum(), 1.0) * 1e-6 / nx          # empty planes still cost a little
     cum = np.concatenate([[0.0], np.cumsum(w)])
-    cuts = [0]
-    for k in range(1, world):
-        c = int(np.searchsorted(cum, cum[-1] * k / world, side="left"))
-        c = min(max(c, cuts[-1] + 1), nx - (world - k))
-        cuts.append(c)
-    cuts.append(nx)
-    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+    def cut(limit):
+        """Greedy slabs of cost <= limit; None if more than `world` are needed."""
+        cuts, lo = [0], 0
+        for k in range(world):
+            left = world - k - 1                   # slabs still to come need a plane each
+            hi = int(np.searchsorted(cum, cum[lo] + limit * (1 + 1e-12), side="right")) - 1
+            if plane_cost > 0.0:
+                hi = min(hi, lo + int(limit / plane_cost))
+            hi = min(max(hi, lo + 1), nx - left)
+            cuts.append(hi)
+            lo = hi
+        return cuts if cuts[-1] >= nx else None
+
+    lo_t = max(cum[-1] / world, plane_cost * nx / world, float(w.max()))
+    hi_t = max(cum[-1], plane_cost * nx)
+    best = cut(hi_t)
+    for _ in range(60):
+        mid = 0.5 * (lo_t + hi_t)
+        c = cut(mid)
+        if c is None:
+            lo_t = mid
+        else:
+            best, hi_t = c, mid
+    best[-1] = nx
+    return [(best[i], best[i + 1]) for i in range(world)]
 
 
 def even_bounds(nx, world):
