@@ -500,8 +500,8 @@ def run_gpu(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             best = float(t) if best is None else min(best, float(t))
         c4 = {"workload": "BASELINE configs[3]: 512^3, 4 bursts, 64 epochs 0-5 yr, 5 GHz flux "
-                          "image per epoch, epochs round-robin over the ranks, all-gather of "
-                          "the images", "ms_total": best, "ms_per_epoch": best / 64,
+                          "image per epoch, epochs round-robin over the ranks (one batched "
+                          "ray walk per rank, rjp_integrate_epochs), all-gather of the images", "ms_total": best, "ms_per_epoch": best / 64,
               "checksum_jy_last_epoch": float(torch.nansum(series[-1]))}
         del series
 

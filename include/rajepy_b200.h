@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RJP_ABI_VERSION 5
+#define RJP_ABI_VERSION 6
 #define RJP_MAX_BURSTS 16
 
 enum {
@@ -306,6 +306,33 @@ int rjp_continuum_images(const double* kff, const double* tsum, const int32_t* t
                          int64_t npix, const double* cff, const double* iff,
                          double omega_jy, int32_t nfreq, double* tau, double* intensity,
                          double* flux, void* stream);
+
+/* Continuum sums for a BATCH of model times in one launch -- the variable-ejection time series
+ * (BASELINE configs[3]): Pipeline repeats the continuum run once per run year with
+ * JetModel.time advanced (classes.py:2347-2453), and the model time enters the integrals only
+ * through the burst factor chi(time - travel time) of each cell (classes.py:861-870,
+ * :399-463).  Every jet-crossing ray is walked once per block of 8 epochs; the cell load, the
+ * travel time and the temperature power are shared by the epochs of a block.
+ *   times  [n_epochs] DEVICE doubles, model times [s] (ep_host->time is ignored; the bursts
+ *          are ep_host's)
+ *   em (optional, may be NULL), kff: [n_epochs][nxs*nz];  tsum, tcount: [nxs*nz] (they do not
+ *          depend on the epoch).  ONLY the pixels of the listed rays are written: the caller
+ *          zero-fills the buffers (rays that miss the jet hold 0, classes.py:1120, :1427).
+ *   travel_cells: optional user-assigned travel-time grid as in rjp_integrate.
+ * Per epoch the result equals rjp_integrate's continuum sums for that model time.          */
+int rjp_integrate_epochs(const rjp_model* m_host, const rjp_epoch* ep_host,
+                         const rjp_continuum* cont_host, const rjp_cell* cells,
+                         const int32_t* extents, const int32_t* ray_list,
+                         const int32_t* n_active, int32_t n_active_hint, const double* times,
+                         int32_t n_epochs, double* em, double* kff, double* tsum,
+                         int32_t* tcount, const double* travel_cells, void* stream);
+
+/* rjp_continuum_images for the K planes of a batch of epochs: kff [n_epochs][npix], tsum /
+ * tcount [npix]; outputs [n_epochs][nfreq][npix] (any may be NULL).                        */
+int rjp_continuum_images_epochs(const double* kff, int32_t n_epochs, const double* tsum,
+                                const int32_t* tcount, int64_t npix, const double* cff,
+                                const double* iff, double omega_jy, int32_t nfreq, double* tau,
+                                double* intensity, double* flux, void* stream);
 
 /* Line-of-sight means of the cell properties for the model plot (replaces the four
  * np.nanmean(<3-D grid>, axis=los) of plotting/functions.py:539-590 and the nanmin / nanmax

@@ -67,9 +67,9 @@ EXPORTS = ("rjp_strerror", "rjp_last_cuda_error", "rjp_abi_version", "rjp_struct
            "rjp_continuum_images", "rjp_voigt_profile", "rjp_brick_count", "rjp_pack_rays",
            "rjp_scatter_rays", "rjp_fill_missed", "rjp_los_means", "rjp_override_cells",
            "rjp_ray_list_chunks", "rjp_host_assemble", "rjp_line_scratch_bytes",
-           "rjp_column_totals")
+           "rjp_column_totals", "rjp_integrate_epochs", "rjp_continuum_images_epochs")
 
-ABI_VERSION = 5      # RJP_ABI_VERSION of include/rajepy_b200.h this binding was written for
+ABI_VERSION = 6      # RJP_ABI_VERSION of include/rajepy_b200.h this binding was written for
 
 
 def library_path():
@@ -136,6 +136,13 @@ def load():
     lib.rjp_scatter_rays.argtypes = [vp, i32, vp, i32, i32, vp, i64, vp]
     lib.rjp_fill_missed.argtypes = [vp, i64, i32, i64, i64, i64, i64, vp, vp, i32, vp]
     lib.rjp_continuum_images.argtypes = [vp, vp, vp, i64, vp, vp, dbl, i32, vp, vp, vp, vp]
+    lib.rjp_integrate_epochs.argtypes = [C.POINTER(Model), C.POINTER(Epoch),
+                                         C.POINTER(Continuum), vp, vp, vp, vp, i32, vp, i32, vp,
+                                         vp, vp, vp, vp, vp]
+    lib.rjp_integrate_epochs.restype = C.c_int
+    lib.rjp_continuum_images_epochs.argtypes = [vp, i32, vp, vp, i64, vp, vp, dbl, i32, vp, vp,
+                                                vp, vp]
+    lib.rjp_continuum_images_epochs.restype = C.c_int
     lib.rjp_voigt_profile.argtypes = [vp, vp, i64, vp, vp]
     lib.rjp_host_assemble.argtypes = [vp, i64, i64, vp, i64, vp, i64, dbl, i32]
     lib.rjp_host_assemble.restype = C.c_int

@@ -33,6 +33,13 @@ int rjp_ray_list_chunk(void);
 int rjp_launch_continuum_images(const double*, const double*, const int32_t*, int64_t,
                                 const double*, const double*, double, int, double*, double*,
                                 double*, cudaStream_t);
+int rjp_launch_continuum_images_epochs(const double*, int, const double*, const int32_t*, int64_t,
+                                       const double*, const double*, double, int, double*,
+                                       double*, double*, cudaStream_t);
+int rjp_launch_integrate_epochs(const rjp_model*, const rjp_epoch*, const rjp_continuum*,
+                                const rjp_cell*, const int32_t*, const int32_t*, const int32_t*,
+                                int, const double*, int, double*, double*, double*, int32_t*,
+                                const double*, cudaStream_t);
 int rjp_launch_voigt_profile(const double*, const double*, int64_t, double*, cudaStream_t);
 int rjp_launch_override(const rjp_model*, const uint8_t*, int32_t, const double*, rjp_cell*,
                         cudaStream_t);
@@ -185,6 +192,37 @@ extern "C" int rjp_continuum_images(const double* kff, const double* tsum,
   return check_launch(rjp_launch_continuum_images(kff, tsum, tcount, npix, cff, iff, omega_jy,
                                                   nfreq, tau, intensity, flux,
                                                   (cudaStream_t)stream));
+}
+
+extern "C" int rjp_continuum_images_epochs(const double* kff, int32_t n_epochs,
+                                           const double* tsum, const int32_t* tcount,
+                                           int64_t npix, const double* cff, const double* iff,
+                                           double omega_jy, int32_t nfreq, double* tau,
+                                           double* intensity, double* flux, void* stream) {
+  if (!kff || !tsum || !tcount || npix < 0 || nfreq < 0 || n_epochs < 0 ||
+      (nfreq > 0 && (!cff || !iff)))
+    return RJP_ERR_ARG;
+  return check_launch(rjp_launch_continuum_images_epochs(kff, n_epochs, tsum, tcount, npix, cff,
+                                                         iff, omega_jy, nfreq, tau, intensity,
+                                                         flux, (cudaStream_t)stream));
+}
+
+extern "C" int rjp_integrate_epochs(const rjp_model* m, const rjp_epoch* ep,
+                                    const rjp_continuum* ct, const rjp_cell* cells,
+                                    const int32_t* extents, const int32_t* ray_list,
+                                    const int32_t* n_active, int32_t n_active_hint,
+                                    const double* times, int32_t n_epochs, double* em,
+                                    double* kff, double* tsum, int32_t* tcount,
+                                    const double* travel_cells, void* stream) {
+  if (!model_ok(m) || !ep || !ct || !cells || !extents || !ray_list || !n_active ||
+      n_epochs < 0 || (n_epochs > 0 && (!times || !kff || !tsum || !tcount)))
+    return RJP_ERR_ARG;
+  if (ep->n_blue < 0 || ep->n_blue > RJP_MAX_BURSTS || ep->n_red < 0 ||
+      ep->n_red > RJP_MAX_BURSTS)
+    return RJP_ERR_ARG;
+  return check_launch(rjp_launch_integrate_epochs(m, ep, ct, cells, extents, ray_list, n_active,
+                                                  n_active_hint, times, n_epochs, em, kff, tsum,
+                                                  tcount, travel_cells, (cudaStream_t)stream));
 }
 
 extern "C" int rjp_voigt_profile(const double* x, const double* y, int64_t n, double* out,

@@ -1462,15 +1462,7 @@ class JetModel:
         freqs = np.atleast_1d(np.asarray(freqs, dtype=np.float64))
         nf = freqs.size
         npix = c["em"].numel()
-        ckey = (freqs.tobytes(), str(dev), float(self._params['properties']['T_0']),
-                float(self._params['power_laws']['q_T']))
-        coeff = _CONT_COEFFS.get(ckey)
-        if coeff is None:
-            coeff = torch.from_numpy(np.stack([self._ff_coeff(freqs),
-                                               2. * freqs ** 2. * con.k / con.c ** 2.])).to(dev)
-            if len(_CONT_COEFFS) > 64:
-                _CONT_COEFFS.clear()
-            _CONT_COEFFS[ckey] = coeff
+        coeff = self._cont_coeff_device(freqs, dev)
         with torch.cuda.device(dev):
             out = torch.empty((nf, npix), dtype=torch.float64, device=dev)
             ptrs = {k: (out.data_ptr() if k == want else None)
@@ -1484,6 +1476,71 @@ class JetModel:
             _cabi.check(st, "rjp_continuum_images")
             _launched()
         return out
+
+    def _cont_coeff_device(self, freqs, dev):
+        """(2, nfreq) device tensor: tau_ff = [0] * K (`_ff_coeff`) and the Rayleigh-Jeans factor
+        2 nu^2 k / c^2 of the intensity (classes.py:1488); cached per frequency list."""
+        torch = _torch()
+        ckey = (freqs.tobytes(), str(dev), float(self._params['properties']['T_0']),
+                float(self._params['power_laws']['q_T']))
+        coeff = _CONT_COEFFS.get(ckey)
+        if coeff is None:
+            coeff = torch.from_numpy(np.stack([self._ff_coeff(freqs),
+                                               2. * freqs ** 2. * con.k / con.c ** 2.])).to(dev)
+            if len(_CONT_COEFFS) > 64:
+                _CONT_COEFFS.clear()
+            _CONT_COEFFS[ckey] = coeff
+        return coeff
+
+    def _continuum_epochs_device(self, times_s, freqs, want='flux', with_em=False):
+        """Continuum images for a BATCH of model times without touching `self.time`: one ray
+        walk for all of them (rjp_integrate_epochs: the epochs only differ in the burst factor
+        chi(t) of each cell, classes.py:861-870) and one epilogue launch.  Returns a device
+        tensor (n_epochs, nfreq, nx_slab * nz) of `want` in ('tau', 'intensity', 'flux')
+        [, the emission measures (n_epochs, nx_slab * nz)]; each epoch equals what
+        `time = t; flux_ff(freqs)` gives."""
+        torch = _torch()
+        lib = _cabi.load()
+        if self._tiles and self._world > 1:
+            raise NotImplementedError("epoch batches are sharded by epoch, not by sky tile")
+        times_s = np.atleast_1d(np.asarray(times_s, dtype=np.float64))
+        freqs = np.atleast_1d(np.asarray(freqs, dtype=np.float64))
+        ne, nf = times_s.size, freqs.size
+        while True:
+            d = self._ensure_filled(sync=False)
+            dev = d["device"]
+            npix = (self._x_hi - self._x_lo) * self._nz
+            with torch.cuda.device(dev):
+                coeff = self._cont_coeff_device(freqs, dev)
+                t_dev = torch.from_numpy(times_s).to(dev, non_blocking=True)
+                kff = torch.zeros((ne, npix), dtype=torch.float64, device=dev)
+                em = torch.zeros((ne, npix), dtype=torch.float64, device=dev) if with_em else None
+                tsum = torch.zeros(npix, dtype=torch.float64, device=dev)
+                cnt = torch.zeros(npix, dtype=torch.int32, device=dev)
+                out = torch.empty((ne, nf, npix), dtype=torch.float64, device=dev)
+                n_hint = self._ray_counts()[0] if ne > 0 else 0
+                st = lib.rjp_integrate_epochs(d["model"], self._epoch_struct(),
+                                              self._continuum_struct(), d["cells"].data_ptr(),
+                                              d["extents"].data_ptr(), d["rays"].data_ptr(),
+                                              d["n_active_dev"].data_ptr(), int(n_hint or 0),
+                                              t_dev.data_ptr(), ne,
+                                              None if em is None else em.data_ptr(),
+                                              kff.data_ptr(), tsum.data_ptr(), cnt.data_ptr(),
+                                              self._cell_grid_ptrs()[0], self._stream())
+                _cabi.check(st, "rjp_integrate_epochs")
+                ptrs = {k: (out.data_ptr() if k == want else None)
+                        for k in ('tau', 'intensity', 'flux')}
+                st = lib.rjp_continuum_images_epochs(kff.data_ptr(), ne, tsum.data_ptr(),
+                                                     cnt.data_ptr(), npix, coeff.data_ptr(),
+                                                     coeff.data_ptr() + nf * 8,
+                                                     self._pixel_solid_angle() / 1e-26, nf,
+                                                     ptrs['tau'], ptrs['intensity'],
+                                                     ptrs['flux'], self._stream())
+                _cabi.check(st, "rjp_continuum_images_epochs")
+                _launched(2)
+            if not self._validate_fill():      # (a host-resolved near-tie changed the state)
+                break
+        return (out, em) if with_em else out
 
     def _sky_sums(self):
         """Tile-sharded models: the four ray sums of the WHOLE sky (EM, K, sum T, count), from
@@ -1880,20 +1937,19 @@ def flux_ff_time_series(params, epochs_s, freq, rank=0, world=1, device=None, lo
     Pipeline does per run year, classes.py:2347-2453): (n_epochs, nx, nz) at frequency `freq`
     for the model times `epochs_s` [s].  Sharded by EPOCH: every rank holds the whole grid
     (epochs only change the burst factor chi(t), the filled state is reused), integrates the
-    epochs `sharding.epoch_shares` deals to it and the images are all-gathered."""
+    epochs `sharding.epoch_shares` deals to it in ONE batched ray walk
+    (`JetModel._continuum_epochs_device`) and the images are all-gathered."""
     from .sharding import epoch_shares, gather_epochs
     torch = _torch()
     epochs_s = np.asarray(epochs_s, dtype=np.float64)
     jm = JetModel(params, log=log, device=device)
-    mine = epoch_shares(len(epochs_s), rank, world)
-    imgs = []
-    for e in mine:
-        jm.time = float(epochs_s[e])
-        imgs.append(jm._continuum_images_device(float(freq), 'flux')[0])
+    mine = list(epoch_shares(len(epochs_s), rank, world))
     dev = jm._device()
     npix = jm.nx * jm.nz
-    local = torch.stack(imgs) if imgs else torch.empty((0, npix), dtype=torch.float64,
-                                                       device=dev)
+    if mine:
+        local = jm._continuum_epochs_device(epochs_s[mine], float(freq), 'flux')[:, 0]
+    else:
+        local = torch.empty((0, npix), dtype=torch.float64, device=dev)
     full = gather_epochs(local, len(epochs_s), rank, world).view(len(epochs_s), jm.nx, jm.nz)
     jm.release()
     return _to_host(full) if host else full

@@ -74,6 +74,54 @@ def test_config4_time_series_driver():
         assert np.array_equal(np.nan_to_num(series[e]), np.nan_to_num(ref))
 
 
+def test_epoch_batch_equals_single_epochs_and_oracle():
+    """rjp_integrate_epochs (one ray walk for a batch of model times, 11 epochs = one full and
+    one partial block of 8) against the per-epoch pass and against the oracle."""
+    from oracle import rajepy_oracle as orc
+    p = cases.with_grid(cases.base_params(), 48, 64, 80)
+    jm, oj = _model(p), orc.OracleJet(cases.with_grid(cases.base_params(), 48, 64, 80))
+    epochs = np.linspace(0., 5., 11) * con.year
+    freqs = np.array([5e9, 43e9])
+    flux, em = jm._continuum_epochs_device(epochs, freqs, 'flux', with_em=True)
+    flux = flux.cpu().numpy().reshape(11, 2, 48, 80)
+    em = em.cpu().numpy().reshape(11, 48, 80)
+    tau = jm._continuum_epochs_device(epochs, freqs, 'tau').cpu().numpy().reshape(11, 2, 48, 80)
+    for e in range(11):
+        jm.time = oj.time = float(epochs[e])
+        one = jm.flux_ff(freqs)
+        assert np.array_equal(np.isnan(flux[e]), np.isnan(one))
+        np.testing.assert_allclose(np.nan_to_num(flux[e]), np.nan_to_num(one), rtol=1e-13,
+                                   atol=0.0)
+        np.testing.assert_allclose(em[e], jm.emission_measure(), rtol=1e-13, atol=0.0)
+        np.testing.assert_allclose(tau[e], jm.optical_depth_ff(freqs), rtol=1e-13, atol=0.0)
+        if e in (0, 4, 10):
+            assert_parity(em[e], oj.emission_measure(), f"EM epoch {e}")
+            assert_parity(tau[e], oj.optical_depth_ff(freqs), f"tau_ff epoch {e}")
+            assert_parity(flux[e], oj.flux_ff(freqs), f"S_ff epoch {e}",
+                          floor=cancellation_floor_ff(oj, freqs))
+
+
+def test_epoch_batch_user_travel_times():
+    """A user-assigned `ts` grid (classes.py:857-859: the setter stores the array the getter
+    subtracts from `time`, i.e. a travel time) is honoured by the batched walk."""
+    p = cases.with_grid(cases.base_params(), 32, 48, 64)
+    jm = _model(p)
+    jm.time = 2.0 * con.year
+    travel = jm.time - jm.ts
+    slower = np.where(np.isnan(travel), np.nan, travel + 0.3 * con.year)
+    jm.ts = slower
+    epochs = np.array([1.0, 2.0, 3.5]) * con.year
+    flux = jm._continuum_epochs_device(epochs, 5e9, 'flux').cpu().numpy().reshape(3, 32, 64)
+    plain = _model(cases.with_grid(cases.base_params(), 32, 48, 64))
+    for e in range(3):
+        jm.time = plain.time = float(epochs[e])
+        one = jm.flux_ff(5e9)
+        assert np.array_equal(np.isnan(flux[e]), np.isnan(one))
+        np.testing.assert_allclose(np.nan_to_num(flux[e]), np.nan_to_num(one), rtol=1e-12,
+                                   atol=0.0)
+    assert not np.allclose(np.nan_to_num(one), np.nan_to_num(plain.flux_ff(5e9)), rtol=1e-6)
+
+
 @pytest.mark.parametrize("n,nch", [(512, 256), (1024, 512)])
 def test_large_grid_properties(n, nch):
     """configs[2] (512^3, 256 channels) and configs[4] (1024^3, 512 channels)."""

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
             "rjp_continuum_images", "rjp_strerror"} <= declared
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in the header but not exported"
-    assert lib.rjp_abi_version() == _cabi.ABI_VERSION == 5
+    assert lib.rjp_abi_version() == _cabi.ABI_VERSION == 6
     assert lib.rjp_strerror(0) == b"ok"
     assert lib.rjp_strerror(-1) == b"invalid argument"
 

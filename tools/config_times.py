@@ -64,6 +64,11 @@ def main():
             series[t] = jm.rt_products(np.array([5e9]), host=False)["flux_ff"]
         jm.release()
 
+    def c4b():
+        p = cases.with_grid(cases.base_params(), 512, 512, 512)
+        series["batched"] = rb.flux_ff_time_series(p, np.linspace(0., 5., 64) * con.year, 5e9,
+                                                   log=log, host=False)
+
     def c5():
         jm = model(0, (1024, 1024, 1024))
         jm.time = con.year
@@ -75,6 +80,8 @@ def main():
             ("C2 256^3, 16 continuum frequencies", c2, 256 ** 3 * 16),
             ("C3 512^3, 256-channel H58a cube", c3, 512 ** 3 * 256),
             ("C4 512^3, 64 epochs x 5 GHz continuum (1 fill + 64 passes)", c4, 512 ** 3 * 64),
+            ("C4 batched: one ray walk for the 64 epochs (flux_ff_time_series)", c4b,
+             512 ** 3 * 64),
             ("C5 1024^3, 16 continuum + 512-channel cube", c5, 1024 ** 3 * 528))
     for name, fn, units in rows:
         fn()
