@@ -271,7 +271,8 @@ class JetModel:
         # x-slabs of equal estimated work (in-jet cells), not equal width: see _plane_weights
         # (a plane of empty sky is not free: its rows of every cube plane are constants to be
         # written, 16 B per ray and channel at ~5.4 TB/s against ~1.05 ns per in-jet cell and
-        # 512 channels of the channel loop, i.e. ~1.45 in-jet cells per ray of the plane)
+        # 512 channels of the channel loop, i.e. ~1.45 in-jet cells per ray of the plane; the
+        # two costs add up, see balanced_bounds)
         self._bounds = balanced_bounds(self._plane_weights(), self._world,
                                        plane_cost=1.45 * self._nz) \
             if (balance and self._world > 1) else even_bounds(self._nx, self._world)

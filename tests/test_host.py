@@ -209,6 +209,30 @@ def test_balanced_bounds_tile_the_grid_and_balance_work():
         sharding.balanced_bounds(np.ones(3), 4)
 
 
+def test_balanced_bounds_minimise_the_busiest_slab():
+    """cost(slab) = in-jet cells + plane_cost x planes (additive); the split is the optimum of
+    an exhaustive search on small cases."""
+    import itertools
+    rng = np.random.default_rng(11)
+    for _ in range(40):
+        nx, world = int(rng.integers(4, 13)), int(rng.integers(2, 5))
+        w = rng.uniform(0, 9, nx) * (rng.random(nx) < 0.4)
+        pc = float(rng.uniform(0, 2))
+        cum = np.concatenate([[0.0], np.cumsum(w + pc)])
+        best = min(max(cum[c[i + 1]] - cum[c[i]] for i in range(world))
+                   for cuts in itertools.combinations(range(1, nx), world - 1)
+                   for c in [(0,) + cuts + (nx,)])
+        b = sharding.balanced_bounds(w, world, plane_cost=pc)
+        got = max(cum[hi] - cum[lo] for lo, hi in b)
+        assert got <= best * (1 + 1e-5) + 1e-9, (w, pc, world, b)
+    # empty sky is not free: a slab of sky only is as expensive as a share of the jet
+    w = np.zeros(1024)
+    w[480:544] = 6e4
+    b = sharding.balanced_bounds(w, 8, plane_cost=1500.0)
+    cost = [w[lo:hi].sum() + 1500.0 * (hi - lo) for lo, hi in b]
+    assert max(cost) <= 1.1 * sum(cost) / 8
+
+
 def test_sharded_models_agree_on_work_balanced_slabs():
     p = cases.with_grid(cases.base_params(), 64, 64, 64)
     slabs = [_model(p, shard=(r, 4)).slab for r in range(4)]
