@@ -221,10 +221,12 @@ int64_t rjp_ray_list_chunks(int64_t nray);
  *   em, kff, tsum [nxs*nz] double, tcount [nxs*nz] int32 (always written)
  *   extents / ray_list / n_active (from rjp_fill_grid / rjp_ray_list); with any of them NULL
  *   (continuum-only passes) every cell of the state is swept instead (dense sweep).
- *   n_active_hint: the caller's guess of *n_active on the HOST, or <= 0 if it has none.  It
- *   only sizes the grid of the line kernel (one CTA per listed ray is fastest); any value
- *   gives correct results, so a count remembered from an earlier model of the same
- *   geometry is fine and nothing has to be read back from the device.
+ *   n_active_hint: the caller's guess of *n_active on the HOST, or < 0 if it has none
+ *   (0 is a count: no ray of the slab crosses the jet, the pass is the constant writer alone).
+ *   It only sizes the grids (one CTA per listed ray is fastest for the line kernel; the
+ *   constant writer gets the SMs the channel loop will not need); any value gives correct
+ *   results, so a count remembered from an earlier model of the same geometry is fine and
+ *   nothing has to be read back from the device.
  *   line/ch may be NULL/nchan = 0 for a continuum-only pass; otherwise
  *   tau_rrl and/or flux_rrl ([nchan][nxs][nz] double) may each be NULL.
  *   contsub: 0 -> flux_rrl includes S_ff (what Pipeline requests, classes.py:2450).

@@ -1472,16 +1472,23 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
   // with TMA bulk stores; launched first so that it is resident beside the ray kernels
   if (!env_int("RJP_SKIP_WRITER", 0)) {   // (debug knob: time the ray kernels alone)
     // beside a channel loop: few CTAs of several warps, so that only a few SMs give up a
-    // slot of the (register-bound) channel loop; alone: one CTA of 4 warps on every SM
-    // With few rays to walk (the outer slabs of a sharded run hold mostly empty sky) the
-    // writer is the longer of the two: size it so that it ends with the channel loop
-    // (measured: ~57 GB/s per CTA of 4 warps, ~6.6e-5 ms per ray x channel of the loop).
+    // slot of the (register-bound) channel loop; alone: one CTA of 4 warps on every SM.
+    // The slabs of a sharded run differ: the outer ones hold mostly sky (the writer is the
+    // longer of the two), the inner ones nearly none.  The writer is sized to end with the
+    // ray kernels.  Measured (tools/slab_probe.py, tools/pass_probe.py): one writer CTA of 4
+    // warps sustains ~57 GB/s; preparation + channel loop cost ~1.05e-6 ms per cell of the
+    // listed rays' extents at 512 channels; a writer CTA on every SM slows the loop by ~1/3.
     int ctas_auto = sms / 4;
     if (lines) {
-      const double t_loop_ms = 6.6e-5 * (double)(n_hint > 0 ? n_hint : (int)(nray / 16)) *
-                               (double)nchan / 512.0 * 8.0;
-      const double bytes = 16.0 * (double)nray * (double)nchan;
-      const double want = bytes / 57e6 / (t_loop_ms > 0.05 ? t_loop_ms : 0.05);
+      // cells of the listed rays: the caller's count (line_max_cells is the summed length of
+      // their extents), else ~63 per ray (BASELINE jet); n_hint = 0 is a count, not "unknown"
+      const double rays = (double)(n_hint >= 0 ? n_hint : (int)(nray / 16));
+      const double cells = (max_cells > 0 && n_hint >= 0) ? (double)max_cells : 63.0 * rays;
+      const double t_loop_ms = 0.05 + 1.05e-6 * cells * (double)nchan / 512.0;
+      const double cta_ms = 16.0 * (double)nray * (double)nchan / 57e6;   // writer work
+      double want = cta_ms / t_loop_ms;
+      for (int it = 0; it < 3; ++it)
+        want = cta_ms / (t_loop_ms * (1.0 + 0.32 * (want < sms ? want : sms) / sms));
       if (want > ctas_auto) ctas_auto = want < sms ? (int)want : sms;
     }
     const int ctas = env_int("RJP_WRITER_CTAS", lines ? ctas_auto : sms);
@@ -1504,7 +1511,8 @@ extern "C" int rjp_launch_integrate(const rjp_model* m, const rjp_epoch* ep,
       return RJP_ERR_CUDA;
     // one CTA per listed ray when the caller knows their number, else a multiple of what fits
     const size_t grid_all = n_hint > 0 ? ((size_t)n_hint < nray ? (size_t)n_hint : nray)
-                                       : (size_t)sms * 8 * (size_t)env_int("RJP_GRID_FACTOR", 16);
+                            : n_hint == 0 ? (size_t)sms
+                                          : (size_t)sms * 8 * (size_t)env_int("RJP_GRID_FACTOR", 16);
     // K4b for the rays [t0, t1) of the list: channel blocks of at most 8 * 256 channels
     auto launch_line = [&](int t0, int t1, size_t grid_rays) {
       const int cblock = env_int("RJP_CHAN_BLOCK", GCH_MAX * LINE_THREADS);   // (experiments)

@@ -270,11 +270,12 @@ class JetModel:
         self._host_ranks = None if host_ranks is None else {int(r) for r in host_ranks}
         # x-slabs of equal estimated work (in-jet cells), not equal width: see _plane_weights
         # (a plane of empty sky is not free: its rows of every cube plane are constants to be
-        # written, 16 B per ray and channel at ~5.4 TB/s against ~1.05 ns per in-jet cell and
-        # 512 channels of the channel loop, i.e. ~1.45 in-jet cells per ray of the plane; the
-        # two costs add up, see balanced_bounds)
+        # written.  Measured per slab at N = 8 (tools/slab_probe.py, 1024^3 x 512 channels):
+        # 1.5 ns per ray of sky (16 B x 512 channels at ~5.5 TB/s) against 1.3 ns per in-jet
+        # cell of the channel loop, i.e. ~1.2 in-jet cells per ray of the plane; the two costs
+        # overlap, but not for free, see balanced_bounds)
         self._bounds = balanced_bounds(self._plane_weights(), self._world,
-                                       plane_cost=1.45 * self._nz) \
+                                       plane_cost=1.2 * self._nz, overlap=0.3) \
             if (balance and self._world > 1) else even_bounds(self._nx, self._world)
         self._x_lo, self._x_hi = self._bounds[self._rank]
         self._dev = None       # dict of device buffers once filled
@@ -1106,7 +1107,7 @@ class JetModel:
             if line is None:
                 st = lib.rjp_integrate(d["model"], ep, ct, d["cells"].data_ptr(),
                                        d["extents"].data_ptr(), d["rays"].data_ptr(),
-                                       d["n_active_dev"].data_ptr(), 0,
+                                       d["n_active_dev"].data_ptr(), -1,
                                        em.data_ptr(), kff.data_ptr(),
                                        tsum.data_ptr(), cnt.data_ptr(), None, None, 0, 1,
                                        None, None, 0, 0, *self._cell_grid_ptrs(), None, 0,

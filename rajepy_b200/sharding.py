@@ -26,40 +26,58 @@ def slab_bounds(nx, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def balanced_bounds(weights, world, plane_cost=0.0):
+def balanced_bounds(weights, world, plane_cost=0.0, overlap=1.0):
     """Contiguous x-slabs [(lo, hi)] * world that minimise the cost of the most expensive slab,
-    cost(slab) = sum of `weights` over its planes + plane_cost * number of planes.
+    cost(slab) = max(L, W) + overlap * min(L, W),  L = sum of `weights` over its planes,
+    W = plane_cost * number of planes.
 
     `weights`: one per x-plane, an estimate of its in-jet cells (the ray walk / channel loop).
     `plane_cost`: what a plane costs even when it is empty sky -- its rows of constants in
-    every cube plane -- in the same unit.  The costs ADD: the constant writer runs beside the
-    channel loop, but on SMs it takes away from it (measured at N = 8 on 1024^3 x 512 channels:
-    a slab with both a full share of the jet and 467 planes of sky took 1.88 ms where the
-    additive split's busiest slab takes 0.89 ms).  The jet occupies a narrow range of x, so
-    equal-width slabs would leave most ranks without any ray to integrate.  Every rank gets
-    >= 1 plane."""
+    every cube plane -- in the same unit.  `overlap`: how much of the shorter of the two a
+    slab pays on top of the longer one: the constant writer runs beside the channel loop
+    (different resources: store bandwidth / instruction issue), but on SMs it shares with it;
+    1 = the costs add, 0 = they hide each other completely (measured ~0.3,
+    tools/slab_probe.py).  The jet occupies a narrow range of x, so equal-width slabs would
+    leave most ranks without any ray to integrate.  Every rank gets >= 1 plane."""
     import numpy as np
     w = np.asarray(weights, dtype=np.float64)
     nx = w.size
     if world < 1 or world > nx:
         raise ValueError("more ranks than x-planes")
-    w = w + float(plane_cost)
-    w = w + max(w.sum(), 1.0) * 1e-6 / nx          # empty planes still cost a little
+    w = w + max(w.sum() + plane_cost * nx, 1.0) * 1e-6 / nx   # empty planes still cost a little
     cum = np.concatenate([[0.0], np.cumsum(w)])
+    pc, ov = float(plane_cost), float(overlap)
+
+    def cost(lo, hi):
+        a, b = cum[hi] - cum[lo], pc * (hi - lo)
+        return max(a, b) + ov * min(a, b)
+
+    def reach(lo, limit, hi_max):
+        """Largest hi <= hi_max with cost(lo, hi) <= limit (cost is monotone in hi), >= lo + 1."""
+        a, b = lo + 1, hi_max
+        if cost(lo, b) <= limit:
+            return b
+        while b - a > 1:                           # invariant: cost(lo, a) <= limit or a = lo + 1
+            m = (a + b) // 2
+            if cost(lo, m) <= limit:
+                a = m
+            else:
+                b = m
+        return a
 
     def cut(limit):
         """Greedy slabs of cost <= limit; None if more than `world` are needed."""
         cuts, lo = [0], 0
         for k in range(world):
-            left = world - k - 1                   # slabs still to come need a plane each
-            hi = int(np.searchsorted(cum, cum[lo] + limit * (1 + 1e-12), side="right")) - 1
-            hi = min(max(hi, lo + 1), nx - left)
+            hi = reach(lo, limit, nx - (world - k - 1))   # slabs still to come need a plane each
+            if cost(lo, hi) > limit:
+                return None
             cuts.append(hi)
             lo = hi
         return cuts if cuts[-1] >= nx else None
 
-    lo_t = max(cum[-1] / world, float(w.max()))
-    hi_t = float(cum[-1])
+    hi_t = cost(0, nx)
+    lo_t = 0.0
     best = cut(hi_t)
     for _ in range(60):
         mid = 0.5 * (lo_t + hi_t)
@@ -68,18 +86,16 @@ def balanced_bounds(weights, world, plane_cost=0.0):
             lo_t = mid
         else:
             best, hi_t = c, mid
-    # the greedy cut packs the leading slabs full and leaves the remainder to the last one:
-    # even the interior cuts out towards the quantiles of the cumulated cost where that does
-    # not raise the maximum
-    best[-1] = nx
-    limit = max(cum[best[i + 1]] - cum[best[i]] for i in range(world))
+    # the greedy cut packs the leading slabs full and leaves the remainder to the last ones:
+    # move the cuts towards the right where that does not raise the maximum, so that the
+    # slack is spread over the slabs
+    limit = max(cost(best[i], best[i + 1]) for i in range(world)) * (1 + 1e-12)
     for k in range(world - 1, 0, -1):
-        want = int(np.searchsorted(cum, cum[-1] * k / world, side="left"))
-        hi_ok = best[k + 1] - 1                    # the slab after the cut keeps a plane
-        c = min(max(want, best[k]), hi_ok)
-        while c > best[k] and cum[c] - cum[best[k - 1]] > limit * (1 + 1e-12):
-            c -= 1
-        best[k] = c
+        # slab k-1 = [best[k-1], best[k]) may grow up to the limit; slab k keeps >= 1 plane
+        far = reach(best[k - 1], limit, best[k + 1] - 1)
+        if far > best[k]:
+            # half way: leaves both neighbours below the limit
+            best[k] = best[k] + (far - best[k]) // 2
     return [(best[i], best[i + 1]) for i in range(world)]
 
 

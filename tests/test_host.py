@@ -210,21 +210,27 @@ def test_balanced_bounds_tile_the_grid_and_balance_work():
 
 
 def test_balanced_bounds_minimise_the_busiest_slab():
-    """cost(slab) = in-jet cells + plane_cost x planes (additive); the split is the optimum of
-    an exhaustive search on small cases."""
+    """cost(slab) = max(L, W) + overlap min(L, W), L = in-jet cells, W = plane_cost x planes;
+    the split is the optimum of an exhaustive search on small cases."""
     import itertools
     rng = np.random.default_rng(11)
-    for _ in range(40):
+    for _ in range(60):
         nx, world = int(rng.integers(4, 13)), int(rng.integers(2, 5))
         w = rng.uniform(0, 9, nx) * (rng.random(nx) < 0.4)
-        pc = float(rng.uniform(0, 2))
-        cum = np.concatenate([[0.0], np.cumsum(w + pc)])
-        best = min(max(cum[c[i + 1]] - cum[c[i]] for i in range(world))
+        pc, ov = float(rng.uniform(0, 2)), float(rng.choice([0.0, 0.3, 1.0]))
+        cum = np.concatenate([[0.0], np.cumsum(w)])
+
+        def cost(lo, hi):
+            a, b = cum[hi] - cum[lo], pc * (hi - lo)
+            return max(a, b) + ov * min(a, b)
+
+        best = min(max(cost(c[i], c[i + 1]) for i in range(world))
                    for cuts in itertools.combinations(range(1, nx), world - 1)
                    for c in [(0,) + cuts + (nx,)])
-        b = sharding.balanced_bounds(w, world, plane_cost=pc)
-        got = max(cum[hi] - cum[lo] for lo, hi in b)
-        assert got <= best * (1 + 1e-5) + 1e-9, (w, pc, world, b)
+        b = sharding.balanced_bounds(w, world, plane_cost=pc, overlap=ov)
+        assert b[0][0] == 0 and b[-1][1] == nx and all(hi > lo for lo, hi in b)
+        got = max(cost(lo, hi) for lo, hi in b)
+        assert got <= best * (1 + 1e-4) + 1e-6, (w, pc, ov, world, b)
     # empty sky is not free: a slab of sky only is as expensive as a share of the jet
     w = np.zeros(1024)
     w[480:544] = 6e4
