@@ -50,6 +50,7 @@ def _torch():
 # zero-filled, which is the state an all-zero occupancy map describes.
 _STATE_POOL = {}
 _PLANE_WEIGHTS = {}     # slab-balancing estimate per geometry (host work, ~20 ms once)
+_SLABS = {}             # balanced slab boundaries per (plane weights, world)
 _LINE_STRUCTS = {}      # line constants + per-channel device arrays
 _TIE_DECISIONS = {}     # host re-decisions of near-tie vertices per (geometry, slab, ties)
 _CONT_COEFFS = {}       # per-frequency continuum coefficients on the device
@@ -274,8 +275,7 @@ class JetModel:
         # 1.5 ns per ray of sky (16 B x 512 channels at ~5.5 TB/s) against 1.3 ns per in-jet
         # cell of the channel loop, i.e. ~1.2 in-jet cells per ray of the plane; the two costs
         # overlap, but not for free, see balanced_bounds)
-        self._bounds = balanced_bounds(self._plane_weights(), self._world,
-                                       plane_cost=1.2 * self._nz, overlap=0.3) \
+        self._bounds = self._balanced_slabs() \
             if (balance and self._world > 1) else even_bounds(self._nx, self._world)
         self._x_lo, self._x_hi = self._bounds[self._rank]
         self._dev = None       # dict of device buffers once filled
@@ -285,6 +285,19 @@ class JetModel:
         self._line = None      # cached line pass
         self._timings = {}
         self._coeff_cache = {}
+
+    def _balanced_slabs(self):
+        """Work-balanced x-slabs of this geometry for `world` ranks; a pure function of the
+        parameters, remembered per geometry (the search is ~ms of host time, a step is too)."""
+        w = self._plane_weights()
+        key = (id(w), self._world, self._nz)
+        hit = _SLABS.get(key)
+        if hit is None or hit[0] is not w:
+            if len(_SLABS) > 64:
+                _SLABS.clear()
+            hit = (w, balanced_bounds(w, self._world, plane_cost=1.2 * self._nz, overlap=0.3))
+            _SLABS[key] = hit
+        return list(hit[1])
 
     def _plane_weights(self):
         """Estimated number of in-jet cells of every x-plane from a coarse sample of cell
