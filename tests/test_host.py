@@ -45,6 +45,60 @@ def test_abi_rejects_bad_arguments_without_gpu():
                                     None, None) == _cabi.ERR_ARG
 
 
+def test_abi_rejects_bad_epoch_batches_without_gpu():
+    lib = _cabi.load()
+    m, ep, ct = _cabi.Model(), _cabi.Epoch(), _cabi.Continuum()
+    assert lib.rjp_integrate_epochs(m, ep, ct, None, None, None, None, 0, None, 4, None, None,
+                                    None, None, None, None) == _cabi.ERR_ARG
+    assert lib.rjp_continuum_images_epochs(None, 3, None, None, 10, None, None, 1.0, 1, None,
+                                           None, None, None) == _cabi.ERR_ARG
+
+
+def _assemble(lib, nchan, plane, ids, cols, fill, threads):
+    out = np.full((nchan, plane), 123.0)
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.float64)
+    st = lib.rjp_host_assemble(out.ctypes.data, nchan, plane, ids.ctypes.data, ids.size,
+                               cols.ctypes.data, cols.shape[1] if cols.ndim == 2 else 0,
+                               float(fill), threads)
+    return st, out
+
+
+@pytest.mark.parametrize("fill", [0.0, np.nan])
+def test_host_assemble_builds_dense_cubes_from_packed_columns(fill):
+    """rjp_host_assemble (host threads, no CUDA call): the dense (nchan, nx*nz) product equals
+    constants + scattered columns, for ragged run patterns, odd alignments and any thread
+    count -- what optical_depth_rrl / flux_rrl hand to numpy (classes.py:1215-1229, :1340-1351)."""
+    lib = _cabi.load()
+    rng = np.random.default_rng(5)
+    for plane, nchan, frac in ((64, 1, 0.5), (1000, 7, 0.06), (4098, 33, 0.3), (130, 5, 1.0),
+                               (2, 3, 0.5), (777, 16, 0.0)):
+        n = int(round(frac * plane))
+        ids = np.sort(rng.choice(plane, size=n, replace=False))
+        if n > 8:                                   # make some long runs of neighbouring rays
+            ids[: n // 2] = ids[0] + np.arange(n // 2)
+            ids = np.unique(ids)
+            n = ids.size
+        cols = rng.normal(size=(nchan, max(n, 1)))
+        if n:
+            cols[0, 0] = np.nan                     # data may hold NaN too
+        want = np.full((nchan, plane), fill)
+        want[:, ids] = cols[:, :n]
+        for threads in (1, 3, 16):
+            st, got = _assemble(lib, nchan, plane, ids, cols, fill, threads)
+            assert st == _cabi.OK
+            assert np.array_equal(got, want, equal_nan=True), (plane, nchan, threads)
+
+
+def test_host_assemble_rejects_bad_ray_lists():
+    lib = _cabi.load()
+    cols = np.zeros((2, 3))
+    for ids in ([3, 2, 5], [1, 1, 2], [0, 4, 10], [-1, 2, 3]):      # not ascending / outside
+        st, _ = _assemble(lib, 2, 10, ids, cols, 0.0, 2)
+        assert st == _cabi.ERR_ARG
+    assert lib.rjp_host_assemble(None, 1, 4, None, 0, None, 0, 0.0, 1) == _cabi.ERR_ARG
+
+
 def test_struct_mirrors_match_header_sizes():
     lib = _cabi.load()
     sizes = [ctypes.c_int32() for _ in range(6)]
