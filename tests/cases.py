@@ -131,6 +131,19 @@ BIG_CASES = {
 }
 
 
+def case_series():
+    """Variable-ejection time series (BASELINE configs[3] in small): the example jet, slightly
+    inclined, 11 model times over 0-5 yr (`SERIES_EPOCHS_YR`), continuum at 5 and 43 GHz.
+    tools/make_golden_series.py runs the unmodified reference once per epoch."""
+    p = with_grid(base_params(), 24, 40, 72)
+    p["geometry"].update({"inc": 80., "pa": 10.})
+    return p
+
+
+SERIES_EPOCHS_YR = np.linspace(0., 5., 11)
+SERIES_FREQS = np.array([5e9, 4.3e10])
+
+
 def pipeline_case():
     """(model params, pipeline params) of the Pipeline-glue fixtures
     (tools/make_golden_pipeline.py): a tiny grid, two epochs x two continuum bands (one with

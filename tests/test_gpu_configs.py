@@ -101,6 +101,34 @@ def test_epoch_batch_equals_single_epochs_and_oracle():
                           floor=cancellation_floor_ff(oj, freqs))
 
 
+def test_epoch_batch_matches_reference_time_series(golden_dir):
+    """The batched walk (and the public flux_ff_time_series driver) against the time series the
+    unmodified reference wrote (tests/golden/series.npz, tools/make_golden_series.py)."""
+    import os
+    import rajepy_b200 as rb
+    from tests.parity import flux_floors_uniform_t
+    g = np.load(os.path.join(golden_dir, "series.npz"))
+    p = cases.case_series()
+    nx, _, nz = (int(v) for v in g["dims"])
+    times = g["epochs_yr"] * con.year
+    jm = _model(p)
+    flux, em = jm._continuum_epochs_device(times, g["freqs"], 'flux', with_em=True)
+    tau = jm._continuum_epochs_device(times, g["freqs"], 'tau')
+    ne, nf = len(times), len(g["freqs"])
+    flux = flux.cpu().numpy().reshape(ne, nf, nx, nz)
+    tau = tau.cpu().numpy().reshape(ne, nf, nx, nz)
+    em = em.cpu().numpy().reshape(ne, nx, nz)
+    floor = flux_floors_uniform_t(p, g["freqs"], p["properties"]["T_0"])[0]
+    for e in range(ne):
+        assert_parity(em[e], g["em"][e], f"EM epoch {e}")
+        assert_parity(tau[e], g["tauff"][e], f"tau_ff epoch {e}")
+        assert_parity(flux[e], g["sff"][e], f"S_ff epoch {e}", floor=floor[:, None, None])
+    series = rb.flux_ff_time_series(cases.case_series(), times, 4.3e10)
+    assert series.shape == (ne, nx, nz)
+    for e in range(ne):
+        assert_parity(series[e], g["sff"][e, 1], f"series epoch {e}", floor=floor[1])
+
+
 def test_epoch_batch_user_travel_times():
     """A user-assigned `ts` grid (classes.py:857-859: the setter stores the array the getter
     subtracts from `time`, i.e. a travel time) is honoured by the batched walk."""

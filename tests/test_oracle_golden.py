@@ -67,6 +67,20 @@ def test_oracle_matches_reference_fixture(name, golden_dir):
         rel_close(oj.flux_rrl(line, chans, contsub=True), g[f"srrl_cs_{e}"], 1e-9)
 
 
+def test_oracle_matches_reference_time_series(golden_dir):
+    """tests/golden/series.npz: 11 model times of a bursting jet, written by the unmodified
+    reference (tools/make_golden_series.py)."""
+    g = np.load(os.path.join(golden_dir, "series.npz"))
+    oj = orc.OracleJet(cases.case_series())
+    assert (oj.nx, oj.ny, oj.nz) == tuple(int(v) for v in g["dims"])
+    assert np.array_equal(g["epochs_yr"], cases.SERIES_EPOCHS_YR)
+    for e, yr in enumerate(g["epochs_yr"]):
+        oj.time = yr * con.year
+        rel_close(oj.emission_measure(), g["em"][e], 1e-12)
+        rel_close(oj.optical_depth_ff(g["freqs"]), g["tauff"][e], 1e-12)
+        rel_close(oj.flux_ff(g["freqs"]), g["sff"][e], 1e-12)
+
+
 def test_survey_smoke_values():
     """Survey-time probe values of the reference."""
     assert orc.gff(5e9, 1e4) == pytest.approx(5.083477778218337, rel=1e-12)
