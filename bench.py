@@ -561,9 +561,11 @@ def run_gpu(args):
         winst = prof.get(f"warp_instructions@{args.grid}x{args.nchan}") if world == 1 else None
         sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
         roof = {"bound": "issue",
-                "kernel": "integration pass: integrate_line_kernel (K3+K4+K5 ray walk, one CTA "
-                          "per jet-crossing ray) || const_tiles_kernel (constant cube planes, "
-                          "TMA bulk stores from 37 CTAs), two streams",
+                "kernel": "integration pass: ray_prepare_kernel (per-cell line constants + "
+                          "continuum sums, one warp per jet-crossing ray) -> integrate_line_kernel "
+                          "(channel loop + flux epilogue, one CTA per jet-crossing ray; the dominant "
+                          "kernel, ~3.8 of the ~4.5 ms) || const_tiles_kernel (constant cube "
+                          "planes, TMA bulk stores), two streams",
                 "achieved": achieved, "peak": hbm, "unit": "GB/s",
                 "frac": achieved / hbm, "traffic": traffic,
                 "peak_source": peak_src, "kernel_ms": float(kms),
