@@ -90,9 +90,11 @@ class ClockSampler:
     timestamps fall between mark_start() and mark_stop() are kept."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,index")
 
     def __init__(self, index):
+        """index: one GPU index or a comma-separated list ("0,1,2,3": every GPU of an N-rank
+        run -- a single throttled GPU sets the max-over-ranks time of the whole job)."""
         self.path = os.path.join(tempfile.mkdtemp(), "clocks.csv")
         self.proc = None
         self.t0 = self.t1 = None
@@ -129,6 +131,7 @@ class ClockSampler:
             self.proc.kill()
         self.f.close()
         sm, smax, reasons, sm_all = [], [], set(), []
+        per_gpu = {}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         with open(self.path) as f:
             for ln in f:
@@ -147,14 +150,20 @@ class ClockSampler:
                 if not inside:
                     continue
                 sm.append(clk)
+                per_gpu.setdefault(parts[8] if len(parts) > 8 else "0", []).append(clk)
                 for nm, v in zip(names, parts[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "samples_whole_run": len(sm_all),
-                "sm_mhz_whole_run": statistics.median(sm_all) if sm_all else None,
-                "reasons": sorted(reasons)}
+        out = {"sm_mhz": statistics.median(sm) if sm else None,
+               "sm_max_mhz": max(smax) if smax else None,
+               "samples": len(sm), "samples_whole_run": len(sm_all),
+               "sm_mhz_whole_run": statistics.median(sm_all) if sm_all else None,
+               "reasons": sorted(reasons)}
+        if len(per_gpu) > 1:
+            # several GPUs were watched: the slowest one bounds a max-over-ranks time
+            out["per_gpu_sm_mhz"] = {g: statistics.median(v) for g, v in sorted(per_gpu.items())}
+            out["sm_mhz_slowest_gpu"] = min(out["per_gpu_sm_mhz"].values())
+        return out
 
 
 # --------------------------------------------------------------------------- CPU arm
@@ -372,7 +381,9 @@ def run_gpu(args):
             return 0, 0.0
         return s_ff.nbytes + t_l.nbytes + s_l.nbytes, float(np.nansum(s_l[len(chans) // 2]))
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    # rank 0 watches every GPU of the job (one node: local ranks 0 .. world-1)
+    sampler = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local) \
+        if rank == 0 else None
     for _ in range(args.warmup):
         out = device_step()
         del out

@@ -62,3 +62,36 @@ def test_clock_sampler_keeps_only_the_timed_window(tmp_path):
     assert out["samples"] == 2 and out["samples_whole_run"] == 4
     assert out["sm_mhz"] == 1957.5 and out["sm_max_mhz"] == 1965.0
     assert out["reasons"] == ["sw_power_cap"]
+
+
+def test_clock_sampler_reports_the_slowest_gpu(tmp_path):
+    """N-rank runs: rank 0 watches every GPU; a GPU whose clock sags shows up by index."""
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ClockSampler.__new__(bench.ClockSampler)
+    s.path = str(tmp_path / "clocks.csv")
+    now = time.time()
+
+    def stamp(t):
+        return time.strftime("%Y/%m/%d %H:%M:%S", time.localtime(t)) + f".{int((t % 1) * 1000):03d}"
+
+    with open(s.path, "wt") as f:
+        for k in range(4):
+            for gpu, clk, therm in ((0, 1965, "Not Active"), (1, 1500, "Active")):
+                f.write(f"{stamp(now + 0.1 + 0.1 * k)}, {clk}, 1965, 700.0, Not Active, "
+                        f"Not Active, {therm}, Not Active, {gpu}\n")
+    s.f = open(s.path)
+    s.t0, s.t1 = now, now + 1.0
+
+    class Done:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+    s.proc = Done()
+    out = s.stop()
+    assert out["samples"] == 8
+    assert out["per_gpu_sm_mhz"] == {"0": 1965.0, "1": 1500.0}
+    assert out["sm_mhz_slowest_gpu"] == 1500.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_thermal_slowdown"]
