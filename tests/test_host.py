@@ -155,6 +155,30 @@ def test_hostmath_matches_oracle_scalars():
     np.testing.assert_array_equal(hm.chan_freqs(1e10, 8e6, 1e6), orc.chan_freqs(1e10, 8e6, 1e6))
 
 
+def test_n_0_from_mlr_known_answer_of_the_reference_tests():
+    """The reference's own known-answer test for this path (test/test_physics.py:38-59):
+    n_0_from_mlr against the quadrature of the mass flux over the jet base, 1e-3 relative, for
+    the 9 x 9 grid of cross-sectional indices -- here for the product's host math AND the
+    oracle (the only golden vectors the reference's tests hold for the path)."""
+    from scipy.integrate import quad
+    msol = 1.989e30
+    mlr, mu, w0, v0, r1, r2 = 1e-6, 1.3, 5.0, 400., 0.5, 5.0
+    const = 2. * con.pi * mu * v0 * 1e3 * hm.atomic_mass("H")
+
+    def flux(w, w0_, qnd_, qnv_, r1_, r2_):
+        return w * (1. + w * (r2_ - r1_) / (w0_ * r1_)) ** (qnd_ + qnv_)
+
+    for qnd in np.linspace(-2, 2, 9):
+        for qnv in np.linspace(-2, 2, 9):
+            integral = quad(flux, 0., w0 * con.au,
+                            args=(w0 * con.au, qnd, qnv, r1 * con.au, r2 * con.au))[0]
+            want = ((mlr * msol / con.year) / (integral * const)) * 1e-6
+            for impl in (hm.n_0_from_mlr, orc.n_0_from_mlr):
+                got = impl(mlr, v0, w0, mu, qnd, qnv, r1, r2)
+                assert abs(got - want) <= 1e-3 * want, (impl.__module__, qnd, qnv, got, want)
+    assert hm.atomic_mass("H") == orc.atomic_mass("H")
+
+
 def test_no_gpu_means_loud_failure():
     import torch
     if torch.cuda.is_available():
