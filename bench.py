@@ -92,7 +92,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap,index")
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=10):
         """index: one GPU index or a comma-separated list ("0,1,2,3": every GPU of an N-rank
         run -- a single throttled GPU sets the max-over-ranks time of the whole job)."""
         self.path = os.path.join(tempfile.mkdtemp(), "clocks.csv")
@@ -102,7 +102,7 @@ class ClockSampler:
             self.f = open(self.path, "wt")
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "10"],
+                 "--format=csv,noheader,nounits", "-lms", str(int(period_ms))],
                 stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -381,9 +381,14 @@ def run_gpu(args):
             return 0, 0.0
         return s_ff.nbytes + t_l.nbytes + s_l.nbytes, float(np.nansum(s_l[len(chans) // 2]))
 
-    # rank 0 watches every GPU of the job (one node: local ranks 0 .. world-1)
-    sampler = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local) \
-        if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 else None
+    # N > 1: a second, slower poll of EVERY GPU of the job (one node: local ranks 0 .. world-1);
+    # a single throttled GPU sets the max-over-ranks time.  Best effort: `clocks` itself stays
+    # the 10 ms poll of rank 0's GPU
+    sampler_all = ClockSampler(",".join(str(i) for i in range(world)), period_ms=25) \
+        if (rank == 0 and world > 1) else None
+    if sampler_all:
+        sampler_all.mark_start()     # (its window includes the warm-up steps: same work)
     for _ in range(args.warmup):
         out = device_step()
         del out
@@ -401,7 +406,15 @@ def run_gpu(args):
     barrier()
     if sampler:
         sampler.mark_stop()
+    if sampler_all:
+        sampler_all.mark_stop()
     clocks = sampler.stop() if sampler else None
+    if sampler_all:
+        every = sampler_all.stop()
+        for key in ("per_gpu_sm_mhz", "sm_mhz_slowest_gpu"):
+            if key in every:
+                clocks[key] = every[key]
+        clocks["reasons_any_gpu"] = every.get("reasons", [])
     launches = jmod.LAUNCHES["count"] - launches0
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     kms = torch.tensor([sum(a.elapsed_time(b) for a, b in kernel_ms) / len(kernel_ms)],
