@@ -81,6 +81,24 @@ def test_oracle_matches_reference_time_series(golden_dir):
         rel_close(oj.flux_ff(g["freqs"]), g["sff"][e], 1e-12)
 
 
+def test_oracle_fuzz_against_the_reference_itself():
+    """Random jets (geometry, all power-law indices, bursts, lines) through the UNMODIFIED
+    reference and the oracle side by side (tools/fuzz_oracle_vs_reference.py; 150 cases are
+    logged in profiles/r2_oracle_fuzz_vs_reference.txt).  Needs /root/reference: build
+    container only."""
+    import subprocess
+    import sys
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference tree not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools",
+                                                       "fuzz_oracle_vs_reference.py"), "6", "3"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "worst relative deviations" in res.stdout
+
+
 def test_survey_smoke_values():
     """Survey-time probe values of the reference."""
     assert orc.gff(5e9, 1e4) == pytest.approx(5.083477778218337, rel=1e-12)
